@@ -1,0 +1,68 @@
+// extern "C" unit-level entry points (mg_op_*): thin wrappers that let the parity tests drive single
+// kernels through the C ABI with plain device pointers. Declared in include/mg_b200.h.
+#include <string>
+
+#include "mg_internal.h"
+#include "mg_b200.h"
+
+namespace mg {
+thread_local std::string g_last_error;
+int set_error(const Error& e) {
+  g_last_error = e.what();
+  return e.code;
+}
+int set_error(const std::exception& e) {
+  g_last_error = e.what();
+  return -100;
+}
+}  // namespace mg
+
+#define MG_API_BEGIN try {
+#define MG_API_END                                      \
+  return 0;                                             \
+  }                                                     \
+  catch (const mg::Error& e) { return mg::set_error(e); } \
+  catch (const std::exception& e) { return mg::set_error(e); }
+
+extern "C" {
+
+const char* mg_last_error(void) { return mg::g_last_error.c_str(); }
+
+int mg_op_gemm(void* stream, int M, int N, int K, const float* a, const float* b, float* c, const float* bias,
+               const float* residual, int act, int planes, int block_n, int ksplit, int swap_out) {
+  MG_API_BEGIN
+  using namespace mg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t ldk = (K + 7) / 8 * 8;
+  bf16 *ah, *al, *bh, *bl;
+  MG_CHECK_CUDA(cudaMallocAsync(&ah, sizeof(bf16) * M * ldk, st));
+  MG_CHECK_CUDA(cudaMallocAsync(&al, sizeof(bf16) * M * ldk, st));
+  MG_CHECK_CUDA(cudaMallocAsync(&bh, sizeof(bf16) * N * ldk, st));
+  MG_CHECK_CUDA(cudaMallocAsync(&bl, sizeof(bf16) * N * ldk, st));
+  launch_split(st, a, M, K, K, Planes{ah, al}, ldk);
+  launch_split(st, b, N, K, K, Planes{bh, bl}, ldk);
+  GemmOperand A, B;
+  A.hi = ah; A.lo = planes == 2 ? al : nullptr; A.rows = M; A.ld = ldk;
+  B.hi = bh; B.lo = planes == 2 ? bl : nullptr; B.rows = N; B.ld = ldk;
+  GemmEpilogue ep;
+  ep.out_f32 = c;
+  if (swap_out) { ep.ld_r = 1; ep.ld_c = M; } else { ep.ld_r = N; ep.ld_c = 1; }
+  ep.bias = bias;
+  ep.act = act;
+  if (ksplit > 1) {
+    // accumulate into c: initialise it with the residual (or zero) first
+    if (residual) MG_CHECK_CUDA(cudaMemcpyAsync(c, residual, sizeof(float) * M * N, cudaMemcpyDeviceToDevice, st));
+    else MG_CHECK_CUDA(cudaMemsetAsync(c, 0, sizeof(float) * M * N, st));
+    ep.atomic = 1;
+  } else {
+    ep.residual = residual;
+  }
+  launch_gemm(st, A, B, M, N, K, 1, 1, ksplit, ep, block_n);
+  MG_CHECK_CUDA(cudaFreeAsync(ah, st));
+  MG_CHECK_CUDA(cudaFreeAsync(al, st));
+  MG_CHECK_CUDA(cudaFreeAsync(bh, st));
+  MG_CHECK_CUDA(cudaFreeAsync(bl, st));
+  MG_API_END
+}
+
+}  // extern "C"

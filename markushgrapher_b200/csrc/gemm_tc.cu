@@ -1,0 +1,392 @@
+// tcgen05 / TMA GEMM for sm_100a:  C[M,N] (+)= A[M,K] * B[N,K]^T, both operands K-major.
+//
+// * Operands are "split planes" (bf16 hi + bf16 lo, see mg_internal.h). With both planes present the
+//   kernel issues three tcgen05.mma products per k-step (hi*hi + hi*lo + lo*hi) into one fp32 TMEM
+//   accumulator, which recovers ~fp32 accuracy (error ~2^-16) from the bf16 tensor pipe. With only the
+//   hi plane it is a plain bf16 GEMM.
+// * Tiles: 128 (M) x BN (N) x 64 (K); TMA (cp.async.bulk.tensor.4d, 128-byte swizzle) stages A/B planes
+//   into a 3-5 deep shared-memory ring guarded by full/empty mbarriers; one elected thread issues the MMAs
+//   (UMMA 128 x BN x 16); the accumulator lives in TMEM and is read back with tcgen05.ld by four epilogue
+//   warps that apply bias / activation / residual and write fp32, split planes, or atomically accumulate
+//   (split-K and residual-stream accumulation for the skinny decode GEMMs).
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
+//
+// Replaces the cuBLAS calls under torch.nn.Linear / torch.matmul in the reference stack
+// (transformers/models/udop/modeling_udop.py:465-468,590,610,617; models/swin/modeling_swin.py:403-405,424,447).
+#include "mg_internal.h"
+#include "ptx.cuh"
+
+namespace mg {
+
+struct alignas(64) GemmParams {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int M, N, K;
+  int nb1;           // blockIdx.z = ks + ksplit * (b1 + nb1 * b2)
+  int ksplit, kb_per_split, num_kb;
+  int a_use1, a_use2, b_use1, b_use2;
+  int nplanes;       // 2 = hi+lo (3 products), 1 = hi only
+  int vec_ok;        // output offsets are 4-element aligned -> vector path allowed
+  GemmEpilogue ep;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU_ERF) return v * 0.5f * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int ks = blockIdx.z % p.ksplit;
+  const int zb = blockIdx.z / p.ksplit;
+  const int b1 = zb % p.nb1;
+  const int b2 = zb / p.nb1;
+  const int kb0 = ks * p.kb_per_split;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  const bool has_work = kb0 < kb1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.ta_hi);
+    prefetch_tmap(&p.tb_hi);
+    if (p.nplanes == 2) {
+      prefetch_tmap(&p.ta_lo);
+      prefetch_tmap(&p.tb_lo);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (has_work) {
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        const int a1 = p.a_use1 ? b1 : 0, a2 = p.a_use2 ? b2 : 0;
+        const int c1 = p.b_use1 ? b1 : 0, c2 = p.b_use2 ? b2 : 0;
+        const uint32_t tx = (p.nplanes == 2) ? C::STAGE_BYTES : (A_BYTES + C::B_BYTES);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], tx);
+          tma_load_4d(st, &p.ta_hi, &full_bar[s], kb * BK, m0, a1, a2);
+          tma_load_4d(st + 2 * A_BYTES, &p.tb_hi, &full_bar[s], kb * BK, n0, c1, c2);
+          if (p.nplanes == 2) {
+            tma_load_4d(st + A_BYTES, &p.ta_lo, &full_bar[s], kb * BK, m0, a1, a2);
+            tma_load_4d(st + 2 * A_BYTES + C::B_BYTES, &p.tb_lo, &full_bar[s], kb * BK, n0, c1, c2);
+          }
+          if (++s == C::STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer (one thread)
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        int s = 0;
+        uint32_t ph = 0;
+        uint32_t acc = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint64_t da_hi = make_sw128_kmajor_desc(sa);
+          const uint64_t da_lo = make_sw128_kmajor_desc(sa + A_BYTES);
+          const uint64_t db_hi = make_sw128_kmajor_desc(sa + 2 * A_BYTES);
+          const uint64_t db_lo = make_sw128_kmajor_desc(sa + 2 * A_BYTES + C::B_BYTES);
+          if (p.nplanes == 2) {
+            // small cross terms first, the dominant hi*hi product last
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, acc);
+              acc = 1;
+            }
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          if (++s == C::STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(tmem_full_bar);  // accumulator complete
+      }
+    } else {
+      // ------------------------------------------------------------------ epilogue (warps 2..5)
+      const GemmEpilogue& ep = p.ep;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int q = warp & 3;  // TMEM lane quadrant this warp may access
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const int64_t row = (row_ok && ep.row_map) ? ep.row_map[m] : m;
+      const int64_t off_b = (int64_t)b1 * ep.bs1 + (int64_t)b2 * ep.bs2;
+      const float bias_m = (row_ok && ep.bias && ep.bias_on_rows) ? ep.bias[m] : 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores below
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int nvalid = min(32, p.N - (n0 + c0));
+        if (ep.bias) {
+          if (ep.bias_on_rows) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bias_m;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += __ldg(ep.bias + n0 + c0 + j);
+          }
+        }
+        if (ep.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+        }
+        const int64_t base = off_b + row * ep.ld_r + (int64_t)(n0 + c0) * ep.ld_c;
+        if (ep.ld_c == 1 && nvalid == 32 && p.vec_ok) {
+          // each thread owns 32 contiguous outputs of its row
+          if (ep.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(ep.out_f32 + base);
+            if (ep.atomic) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                atomicAdd(dst + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            } else {
+              if (ep.residual) {
+                const float4* res = reinterpret_cast<const float4*>(ep.residual + base);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = res[j];
+                  v[4 * j] += t.x;
+                  v[4 * j + 1] += t.y;
+                  v[4 * j + 2] += t.z;
+                  v[4 * j + 3] += t.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          } else {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              bf16 h0, l0, h1, l1;
+              split_bf16(v[2 * j], h0, l0);
+              split_bf16(v[2 * j + 1], h1, l1);
+              hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + base);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            if (ep.out_lo) {
+              uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + base);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        } else {
+          // generic path: scalar, coalesced across lanes when ld_r == 1 (swapped-operand GEMMs)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              const int64_t o = base + (int64_t)j * ep.ld_c;
+              float x = v[j];
+              if (ep.out_f32) {
+                if (ep.atomic) {
+                  atomicAdd(ep.out_f32 + o, x);
+                } else {
+                  if (ep.residual) x += ep.residual[o];
+                  ep.out_f32[o] = x;
+                }
+              } else {
+                bf16 h, l;
+                split_bf16(x, h, l);
+                ep.out_hi[o] = h;
+                if (ep.out_lo) ep.out_lo[o] = l;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    MG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    MG_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static void encode_operand(CUtensorMap* map, const bf16* ptr, const GemmOperand& op, int K, int nb1, int nb2,
+                           int box_rows) {
+  MG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand must be 16-byte aligned");
+  MG_REQUIRE(op.ld % 8 == 0, "GEMM operand row stride must be a multiple of 8 elements");
+  const cuuint64_t d1 = op.use_b1 ? nb1 : 1, d2 = op.use_b2 ? nb2 : 1;
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)op.rows, d1, d2};
+  const cuuint64_t dflt = (cuuint64_t)op.ld * 2 * (cuuint64_t)(op.rows > 0 ? op.rows : 1);
+  cuuint64_t s1 = op.use_b1 ? (cuuint64_t)op.bs1 * 2 : dflt;
+  cuuint64_t s2 = op.use_b2 ? (cuuint64_t)op.bs2 * 2 : dflt;
+  MG_REQUIRE(s1 % 16 == 0 && s2 % 16 == 0, "GEMM operand batch strides must be multiples of 8 elements");
+  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 2, s1, s2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(ptr), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(-3, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r) + " (K=" +
+                        std::to_string(K) + " rows=" + std::to_string(op.rows) + " ld=" + std::to_string(op.ld) + ")");
+}
+
+template <int BN>
+static void launch_bn(cudaStream_t st, const GemmParams& p, dim3 grid) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(p);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_gemm(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int nb1, int nb2,
+                 int ksplit, const GemmEpilogue& ep, int block_n) {
+  MG_REQUIRE(M > 0 && N > 0 && K > 0 && nb1 > 0 && nb2 > 0, "empty GEMM");
+  MG_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "block_n must be 32, 64 or 128");
+  MG_REQUIRE((A.lo != nullptr) == (B.lo != nullptr), "both operands must have the same number of planes");
+  MG_REQUIRE(ksplit >= 1 && (ksplit == 1 || (ep.atomic && ep.out_f32)), "split-K needs the atomic fp32 epilogue");
+  MG_REQUIRE((ep.out_f32 != nullptr) != (ep.out_hi != nullptr), "exactly one output kind");
+  MG_REQUIRE(A.rows >= M && B.rows >= N, "operand has fewer rows than the problem");
+  GemmParams p;
+  p.nplanes = A.lo ? 2 : 1;
+  encode_operand(&p.ta_hi, A.hi, A, K, nb1, nb2, BM);
+  encode_operand(&p.tb_hi, B.hi, B, K, nb1, nb2, block_n);
+  if (p.nplanes == 2) {
+    encode_operand(&p.ta_lo, A.lo, A, K, nb1, nb2, BM);
+    encode_operand(&p.tb_lo, B.lo, B, K, nb1, nb2, block_n);
+  } else {
+    p.ta_lo = p.ta_hi;
+    p.tb_lo = p.tb_hi;
+  }
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.nb1 = nb1;
+  p.num_kb = (K + BK - 1) / BK;
+  if (ksplit > p.num_kb) ksplit = p.num_kb;
+  p.kb_per_split = (p.num_kb + ksplit - 1) / ksplit;
+  ksplit = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.ksplit = ksplit;
+  p.a_use1 = A.use_b1;
+  p.a_use2 = A.use_b2;
+  p.b_use1 = B.use_b1;
+  p.b_use2 = B.use_b2;
+  p.ep = ep;
+  const void* optr = ep.out_f32 ? (const void*)ep.out_f32 : (const void*)ep.out_hi;
+  const int align_el = ep.out_f32 ? 4 : 8;  // 16-byte vectors
+  p.vec_ok = (ep.ld_c == 1) && (ep.ld_r % align_el == 0) && (ep.bs1 % align_el == 0) && (ep.bs2 % align_el == 0) &&
+             ((reinterpret_cast<uintptr_t>(optr) & 15) == 0) &&
+             (!ep.out_lo || (reinterpret_cast<uintptr_t>(ep.out_lo) & 15) == 0) &&
+             (!ep.residual || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
+  dim3 grid((N + block_n - 1) / block_n, (M + BM - 1) / BM, ksplit * nb1 * nb2);
+  MG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "GEMM grid too large");
+  if (block_n == 128)
+    launch_bn<128>(st, p, grid);
+  else if (block_n == 64)
+    launch_bn<64>(st, p, grid);
+  else
+    launch_bn<32>(st, p, grid);
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 -> planes
+__global__ void split_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in, bf16* hi,
+                             bf16* lo, int64_t ld_out) {
+  const int64_t total = rows * ld_out;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_out, c = i % ld_out;
+    const float x = c < cols ? in[r * ld_in + c] : 0.f;
+    bf16 h, l;
+    split_bf16(x, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+void launch_split(cudaStream_t st, const float* in, int64_t rows, int64_t cols, int64_t ld_in, Planes out,
+                  int64_t ld_out) {
+  const int64_t total = rows * ld_out;
+  if (total == 0) return;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  split_kernel<<<blocks, 256, 0, st>>>(in, rows, cols, ld_in, out.hi, out.lo, ld_out);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace mg
