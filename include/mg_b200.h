@@ -1,4 +1,25 @@
-/* mg_b200.h — C ABI of libmg_b200.so (work in progress header; see bottom of file for the model API). */
+/* mg_b200.h — C ABI of libmg_b200.so: the B200-native forward+generate hot path of MarkushGrapher-2
+ * (Swin-B OCSR encoder -> MLP projector -> UDOP vision-text-layout encoder -> T5 decoder, greedy decode).
+ *
+ * The reference has no FFI for this path: its interface is the Python object contract of the (un-vendored)
+ * transformers-fork class MarkushgrapherForConditionalGeneration as exercised by markushgrapher.core
+ * (SURVEY.md §8b). Each entry point below names the reference call it stands behind:
+ *
+ *   mg_create / mg_load_weight / mg_finalize  <- MarkushgrapherForConditionalGeneration(config) /
+ *        .from_pretrained(path, config=config).to(device)   reference markushgrapher/core/common/begin.py:128-133
+ *        model.init_molscribe_weights() / model.safe_load() reference begin.py:138,151,166
+ *   mg_encode          <- model.encoder(...) inside generate (encode once)
+ *                         transformers/generation/utils.py:765-803, models/udop/modeling_udop.py:1064-1256
+ *   mg_generate(_host) <- model.generate(input_ids=, bbox=, pixel_values=, labels=, num_beams=, max_length=)
+ *                         reference markushgrapher/utils/ocsr/utils_evaluation.py:269-285
+ *   mg_forward_logits  <- model(**batch).logits   reference markushgrapher/core/trainers/curriculumTrainer.py:655
+ *
+ * Conventions: every function returns 0 on success or a negative error code; the message is available from
+ * mg_last_error() (thread-local). Unless a parameter says "host", pointers are DEVICE pointers (e.g.
+ * torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as void*. Calls are asynchronous on `stream`
+ * except where stated. One mg_model per device; not thread-safe across concurrent calls on the same model.
+ * The library never allocates caller-visible memory. No torch / C++ types cross this boundary.
+ */
 #ifndef MG_B200_H
 #define MG_B200_H
 #include <stdint.h>
@@ -6,12 +27,76 @@
 extern "C" {
 #endif
 
-const char* mg_last_error(void);
+#define MG_MAX_SWIN_STAGES 4
 
-/* c[M,N] = act(a[M,K] * b[N,K]^T + bias[N]) + residual[M,N]; fp32 device pointers, row-major.
+typedef struct mg_config {
+  /* UDOP / T5 dims (transformers/models/udop/configuration_udop.py) */
+  int32_t vocab_size, d_model, d_kv, d_ff, num_layers, num_decoder_layers, num_heads;
+  int32_t rel_buckets, rel_max_distance, max_2d, image_size, patch_size;
+  float ln_eps;
+  /* OCSR Swin encoder (MolScribe swin_base_patch4_window12_384 geometry) */
+  int32_t swin_image, swin_patch, swin_embed, swin_num_stages;
+  int32_t swin_depths[MG_MAX_SWIN_STAGES], swin_heads[MG_MAX_SWIN_STAGES];
+  int32_t swin_window;
+  float swin_ln_eps;
+  int32_t proj_hidden;
+  /* numerics: 0 = fp32-parity (split-bf16 tensor-core GEMMs, ~2^-16), 1 = plain bf16 GEMM inputs */
+  int32_t precision;
+  float logit_scale; /* d_model^-0.5 for the tied-head UDOP convention, 1.0 otherwise */
+  int32_t decoder_start_token_id, eos_token_id, pad_token_id;
+  int32_t enc_chunk; /* images per encoder pass (bounds the S x S score scratch); 0 = default 64 */
+} mg_config;
+
+typedef struct mg_model mg_model;
+
+const char* mg_last_error(void);
+/* 1 if a CUDA device is visible to the library, else 0 (no compute is attempted) */
+int mg_device_available(void);
+
+int mg_create(const mg_config* cfg, mg_model** out);
+void mg_destroy(mg_model* m);
+
+/* Register one fp32 parameter by its state_dict name (HF naming of the stock UDOP/Swin modules, see
+ * INTEGRATION.md). dtype: 0 = fp32 (only value accepted). The pointer is borrowed until mg_finalize returns.
+ * Returns 1 (not an error) if the name is not used by the path. */
+int mg_load_weight(mg_model* m, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int rank);
+/* Repack all weights into the library's own layouts (split planes, fused QKV, ...). Synchronises `stream`.
+ * After it returns the caller may free its tensors. */
+int mg_finalize(mg_model* m, void* stream);
+
+/* Encoder: input_ids (B,Lt) i64, bbox (B,Lt,4) f32 in [0,1], pixel_values (B,3,image,image) f32,
+ * attn_mask (B,Lt) i64 or NULL. Writes enc_out (B, M, d_model) f32 and enc_mask (B, M) i32 if non-NULL, with
+ * M = swin_tokens + Lt + (image/patch)^2 (reported through M_out, host pointer, may be NULL). */
+int mg_encode(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+              const float* pixel_values, const int64_t* attn_mask, float* enc_out, int32_t* enc_mask, int32_t* M_out);
+
+/* Greedy generate (num_beams must be 1 in this revision). out_ids (B, max_length) i64: column 0 = decoder start id,
+ * finished rows padded with pad id. out_len (B) i32 = tokens up to and including EOS (or the columns generated).
+ * step_logits: NULL or (B, max_length-1, vocab) f32 receiving the logits of every step (debug / parity).
+ * steps_run (host, may be NULL): number of decode steps executed. Synchronises `stream` before returning. */
+int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length, int64_t* out_ids,
+                int32_t* out_len, float* step_logits, int32_t* steps_run);
+
+/* Same, but every buffer is a HOST pointer (pinned memory recommended): inputs are copied host->device and the
+ * ids device->host inside the call. This is the end-to-end entry the reference's generate() call maps to. */
+int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                     const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length,
+                     int64_t* out_ids, int32_t* out_len, int32_t* steps_run);
+
+/* statistics of the last mg_generate call (host pointers, any may be NULL) */
+int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);
+
+/* ---- unit-level entry points used by the parity tests (device pointers, fp32) ---- */
+
+/* c[M,N] = act(a[M,K] * b[N,K]^T + bias[N]) + residual[M,N]; row-major.
  * planes: 2 = split-bf16 (near-fp32), 1 = plain bf16. swap_out: write c transposed ([N,M] row-major). */
 int mg_op_gemm(void* stream, int M, int N, int K, const float* a, const float* b, float* c, const float* bias,
                const float* residual, int act, int planes, int block_n, int ksplit, int swap_out);
+
+/* HOST-only: T5/UDOP relative-position bucket LUT, lut[n] = bucket of |relative_position| = n without the
+ * bidirectional sign offset (transformers/models/udop/modeling_udop.py:466-512). Needs no GPU. */
+int mg_rel_bucket_lut(int bidirectional, int num_buckets, int max_distance, int n_entries, int32_t* lut_host);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,316 @@
+// Autoregressive decode-step kernels (T5/UDOP decoder, one new token per image per step):
+// fused KV-cache append + self-attention with the T5 unidirectional bucket bias, cross-attention over the
+// encoder memory, ReLU+split, LM-head argmax with finished-row bookkeeping and next-token embedding.
+// Every kernel reads the current step from a device counter so one captured CUDA graph replays for all steps.
+// Arithmetic follows transformers/models/udop/modeling_udop.py (UdopAttention.forward :531-622,
+// compute_bias :514-529, UdopStack decoder path :1146-1256, lm head :1585-1590) and
+// transformers/generation/utils.py::_sample (:2762-2805).
+#include <algorithm>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace mg {
+
+// =====================================================================================================
+// Single-query attention for one (head, image).   HD = 64.
+//   K^T cache : kt[b][h*64 + d][key]   (row stride kt_ld, image stride kt_bs)   -> coalesced over keys
+//   V   cache : v [b][key][h*64 + d]   (row stride v_ld,  image stride v_bs)    -> coalesced over d
+// SELF : n_keys = step+1; the new k/v row (from the fused QKV GEMM output qkv[b][3*D]) is appended to the
+//        caches by this kernel and used from shared memory; bias = dec_bias[lut[step - j]][h].
+// CROSS: n_keys = Mp; additive mask (1-mask)*finfo.min, no positional bias (:588-593).
+// Scores are NOT scaled by 1/sqrt(d) (T5).  Output ctx[b][h*64+d] is written as split planes for the O GEMM.
+template <bool SELF>
+__global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qsrc, int q_ld, float* __restrict__ kt,
+                                                       int64_t kt_ld, int64_t kt_bs, float* __restrict__ v,
+                                                       int64_t v_ld, int64_t v_bs, const int* __restrict__ step_ptr,
+                                                       int n_keys_cross, const int* __restrict__ mask, int mask_ld,
+                                                       const float* __restrict__ dec_bias, const int* __restrict__ lut,
+                                                       int H, int D, bf16* __restrict__ ctx_hi,
+                                                       bf16* __restrict__ ctx_lo) {
+  constexpr int HD = 64;
+  extern __shared__ __align__(16) float sm[];
+  float* sq = sm;             // [64]
+  float* snew = sq + HD;      // [64] new v row (self)
+  float* sred = snew + HD;    // [16*64] PV partials / reductions
+  float* sc = sred + 16 * HD; // [n_keys padded to 4]
+  __shared__ float s_bcast[2];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int step = SELF ? *step_ptr : 0;
+  const int nk = SELF ? step + 1 : n_keys_cross;
+  const int ncache = SELF ? step : nk;  // keys already resident in the caches
+  float* ktb = kt + (int64_t)b * kt_bs + (int64_t)h * HD * kt_ld;
+  float* vb = v + (int64_t)b * v_bs + (int64_t)h * HD;
+
+  if (tid < HD) {
+    sq[tid] = qsrc[(int64_t)b * q_ld + h * HD + tid];
+    if (SELF) {
+      const float kn = qsrc[(int64_t)b * q_ld + D + h * HD + tid];
+      const float vn = qsrc[(int64_t)b * q_ld + 2 * D + h * HD + tid];
+      snew[tid] = vn;
+      ktb[(int64_t)tid * kt_ld + step] = kn;  // append
+      vb[(int64_t)step * v_ld + tid] = vn;
+      sred[tid] = sq[tid] * kn;  // partial products of q . k_new
+    }
+  }
+  __syncthreads();
+  // ---- scores over cached keys: thread = 4 consecutive keys, loop over d (coalesced float4 rows of K^T)
+  const int n4 = ncache >> 2;
+  for (int g = tid; g < n4; g += 256) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* col = reinterpret_cast<const float4*>(ktb) + g;
+    const int64_t ld4 = kt_ld >> 2;
+#pragma unroll 16
+    for (int d = 0; d < HD; ++d) {
+      const float4 kk = __ldg(col + d * ld4);
+      const float qd = sq[d];
+      a.x += qd * kk.x; a.y += qd * kk.y; a.z += qd * kk.z; a.w += qd * kk.w;
+    }
+    reinterpret_cast<float4*>(sc)[g] = a;
+  }
+  for (int j = (n4 << 2) + tid; j < ncache; j += 256) {  // ragged tail (self only: ncache = step)
+    float a = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < HD; ++d) a += sq[d] * ktb[(int64_t)d * kt_ld + j];
+    sc[j] = a;
+  }
+  if (SELF && tid == 0) {
+    float a = 0.f;
+    for (int d = 0; d < HD; ++d) a += sred[d];
+    sc[step] = a;
+  }
+  __syncthreads();
+  // ---- bias / mask, max
+  float mx = -INFINITY;
+  for (int j = tid; j < nk; j += 256) {
+    float s = sc[j];
+    if (SELF) {
+      s += dec_bias[lut[step - j] * H + h];  // causal mask is all-visible for the newest token
+    } else {
+      s += (mask[(int64_t)b * mask_ld + j] ? 0.f : -3.4028234663852886e38f);
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float* wred = sred + 64;  // [8] scratch (sred[0..63] no longer needed)
+  if ((tid & 31) == 0) wred[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m = wred[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, wred[i]);
+    s_bcast[0] = m;
+  }
+  __syncthreads();
+  mx = s_bcast[0];
+  float sum = 0.f;
+  for (int j = tid; j < nk; j += 256) {
+    const float p = expf(sc[j] - mx);
+    sc[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((tid & 31) == 0) wred[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += wred[i];
+    s_bcast[1] = s;
+  }
+  __syncthreads();
+  const float inv = 1.f / s_bcast[1];
+  // ---- P.V: thread (r = tid/16, c = tid%16) accumulates float4 column c over keys j == r (mod 16)
+  const int r = tid >> 4, c = tid & 15;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* v4 = reinterpret_cast<const float4*>(vb) + c;
+  const int64_t vld4 = v_ld >> 2;
+#pragma unroll 4
+  for (int j = r; j < ncache; j += 16) {
+    const float4 vv = __ldg(v4 + (int64_t)j * vld4);
+    const float p = sc[j];
+    acc.x += p * vv.x; acc.y += p * vv.y; acc.z += p * vv.z; acc.w += p * vv.w;
+  }
+  if (SELF && r == 0) {
+    const float p = sc[step];
+    acc.x += p * snew[4 * c]; acc.y += p * snew[4 * c + 1]; acc.z += p * snew[4 * c + 2]; acc.w += p * snew[4 * c + 3];
+  }
+  __syncthreads();
+  reinterpret_cast<float4*>(sred)[r * 16 + c] = acc;
+  __syncthreads();
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) o += sred[rr * HD + tid];
+    o *= inv;
+    bf16 hh, ll;
+    split_bf16(o, hh, ll);
+    ctx_hi[(int64_t)b * D + h * HD + tid] = hh;
+    if (ctx_lo) ctx_lo[(int64_t)b * D + h * HD + tid] = ll;
+  }
+}
+
+static size_t dec_attn_smem(int max_keys) { return (size_t)(64 + 64 + 16 * 64 + ((max_keys + 3) / 4) * 4) * sizeof(float); }
+
+void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D, float* kt, int64_t kt_ld,
+                          int64_t kt_bs, float* v, int64_t v_ld, int64_t v_bs, const int* step_ptr, int max_keys,
+                          const float* dec_bias, const int* lut, Planes ctx) {
+  MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
+  dim3 grid(H, B);
+  dec_attn_kernel<true><<<grid, 256, dec_attn_smem(max_keys), st>>>(qkv, 3 * D, kt, kt_ld, kt_bs, v, v_ld, v_bs,
+                                                                     step_ptr, 0, nullptr, 0, dec_bias, lut, H, D,
+                                                                     ctx.hi, ctx.lo);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
+                           int64_t kt_bs, const float* v, int64_t v_ld, int64_t v_bs, int n_keys, const int* mask,
+                           int mask_ld, Planes ctx) {
+  MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
+  MG_REQUIRE(n_keys % 4 == 0 && kt_ld % 4 == 0, "cross-attention memory length must be a multiple of 4");
+  dim3 grid(H, B);
+  dec_attn_kernel<false><<<grid, 256, dec_attn_smem(n_keys), st>>>(q, D, const_cast<float*>(kt), kt_ld, kt_bs,
+                                                                   const_cast<float*>(v), v_ld, v_bs, nullptr, n_keys,
+                                                                   mask, mask_ld, nullptr, nullptr, H, D, ctx.hi,
+                                                                   ctx.lo);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// h = relu(x) -> split planes (decode FF: the wi GEMM is split-K/atomic so the activation cannot live in its epilogue)
+__global__ void relu_split_kernel(const float* __restrict__ x, int64_t n, bf16* hi, bf16* lo) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    bf16 h, l;
+    split_bf16(fmaxf(x[i], 0.f), h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out) {
+  if (!n) return;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  relu_split_kernel<<<blocks, 256, 0, st>>>(x, n, out.hi, out.lo);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// Greedy selection (GenerationMixin._sample :2762-2805): first-max argmax over fp32 logits, finished rows
+// emit pad, EOS bookkeeping, token append, next-step input embedding.  One CTA per image.  The last CTA to
+// finish advances the device step counter and publishes the "all rows finished" flag.
+__global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ logits, int V, int64_t ld,
+                                                            const float* __restrict__ emb, int D, int eos, int pad,
+                                                            int64_t* __restrict__ out_ids, int out_ld,
+                                                            int* __restrict__ finished, int* __restrict__ step_ptr,
+                                                            int* __restrict__ n_unfinished, int* __restrict__ ticket,
+                                                            float* __restrict__ x_next, float* __restrict__ logits_dump,
+                                                            int64_t dump_bs, int64_t dump_ss) {
+  const int b = blockIdx.x;
+  const float* lg = logits + (int64_t)b * ld;
+  const int step = *step_ptr;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float x = lg[i];
+    if (logits_dump) logits_dump[(int64_t)b * dump_bs + (int64_t)step * dump_ss + i] = x;
+    if (x > best || (x == best && i < bi)) {
+      best = x;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  __shared__ float sb[8];
+  __shared__ int si[8];
+  __shared__ int s_tok;
+  if ((threadIdx.x & 31) == 0) {
+    sb[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sb[w] > best || (sb[w] == best && si[w] < bi)) {
+        best = sb[w];
+        bi = si[w];
+      }
+    const int fin = finished[b];
+    const int tok = fin ? pad : bi;
+    out_ids[(int64_t)b * out_ld + step + 1] = tok;
+    if (!fin && tok == eos) {
+      finished[b] = 1;
+      atomicSub(n_unfinished, 1);
+    }
+    s_tok = tok;
+  }
+  __syncthreads();
+  const int tok = s_tok;
+  const float4* e4 = reinterpret_cast<const float4*>(emb + (int64_t)tok * D);
+  float4* x4 = reinterpret_cast<float4*>(x_next + (int64_t)b * D);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) x4[c] = e4[c];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int t = atomicAdd(ticket, 1);
+    if (t == (int)gridDim.x - 1) {
+      *ticket = 0;
+      *step_ptr = step + 1;
+    }
+  }
+}
+
+void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
+                          int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
+                          int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
+                          int64_t dump_ss) {
+  greedy_select_kernel<<<B, 256, 0, st>>>(logits, V, ld, emb, D, eos, pad, out_ids, out_ld, finished, step_ptr,
+                                          n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// decode state reset: ids[:,0] = start token, x = emb[start], finished = 0, step = 0
+__global__ void decode_init_kernel(const float* __restrict__ emb, int D, int start, int B, int64_t* out_ids, int out_ld,
+                                   int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < out_ld; i += blockDim.x) out_ids[(int64_t)b * out_ld + i] = (i == 0) ? start : 0;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) x[(int64_t)b * D + c] = emb[(int64_t)start * D + c];
+  if (threadIdx.x == 0) {
+    finished[b] = 0;
+    if (b == 0) {
+      *step_ptr = 0;
+      *n_unfinished = B;
+      *ticket = 0;
+    }
+  }
+}
+void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int B, int64_t* out_ids, int out_ld,
+                        int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x) {
+  decode_init_kernel<<<B, 256, 0, st>>>(emb, D, start, B, out_ids, out_ld, finished, step_ptr, n_unfinished, ticket, x);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// per-row output length: index of the first EOS + 1, else ncols
+__global__ void out_len_kernel(const int64_t* __restrict__ ids, int B, int ld, int ncols, int eos, int* __restrict__ len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = ncols;
+  for (int t = 1; t < ncols; ++t)
+    if (ids[(int64_t)b * ld + t] == eos) {
+      n = t + 1;
+      break;
+    }
+  len[b] = n;
+}
+void launch_out_len(cudaStream_t st, const int64_t* ids, int B, int ld, int ncols, int eos, int* len) {
+  out_len_kernel<<<(B + 127) / 128, 128, 0, st>>>(ids, B, ld, ncols, eos, len);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace mg

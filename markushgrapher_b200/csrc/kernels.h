@@ -1,0 +1,50 @@
+// Launch wrappers of all non-GEMM kernels (definitions in ops.cu / swin.cu / decode.cu).
+#pragma once
+#include "mg_internal.h"
+
+namespace mg {
+
+// ---- ops.cu
+void rel_bucket_lut(int bidirectional, int num_buckets, int max_distance, int n_entries, int32_t* lut);
+void launch_rmsnorm(cudaStream_t st, const float* x, const float* w, int64_t rows, int D, float eps, float scale,
+                    Planes out, float* out_f32, int64_t rows_per_b, int64_t out_bs, int64_t out_off);
+void launch_im2col(cudaStream_t st, const float* px, int B, int H, int W, int p, int ldk, Planes out);
+void launch_combine(cudaStream_t st, const int64_t* ids, const float* bbox, const int64_t* attn_mask,
+                    const float* tok_emb, const float* patch_emb, const float* cell_x, const float* cell_y, int B,
+                    int Lt, int np, int Sp, int D, int max_2d, int vocab, int* ocr_point, int* vis_src, int* n_vis,
+                    float* x, double* bbox_ext, int* mask);
+void launch_relbucket_hv(cudaStream_t st, const double* bbox_ext, int B, int Sp, const int* lut_hv, int lut_n,
+                         int half_buckets, uchar2* hv);
+void launch_enc_softmax(cudaStream_t st, const float* scores, const uchar2* hv, const int* mask, const float* tab1d,
+                        const float* tabh, const float* tabv, const int* lut1d, int lut1d_n, int half_buckets,
+                        int nbuckets, int B, int H, int Sp, Planes P);
+void launch_fill_f32(cudaStream_t st, float* p, int64_t n, float v);
+void launch_build_mem_mask(cudaStream_t st, const int* vtl_mask, int B, int Sp, int S, int n_sw, int Mp, int* out);
+
+// ---- swin.cu
+void launch_resize_bilinear(cudaStream_t st, const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* out);
+void launch_window_rowmap(cudaStream_t st, int B, int Hs, int Ws, int ws, int shift, int* map);
+void launch_merge_rowmap(cudaStream_t st, int B, int Hs, int Ws, int* map);
+void launch_layernorm_any(cudaStream_t st, const float* x, const int* src_rows, int G, int C, int64_t rows,
+                          const float* w, const float* b, float eps, Planes out, float* out_f32);
+void launch_window_attn(cudaStream_t st, const float* qkv, const float* table, int64_t n_windows, int C, int heads,
+                        int ws, int Hs, int Ws, int shift, Planes out);
+
+// ---- decode.cu
+void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D, float* kt, int64_t kt_ld,
+                          int64_t kt_bs, float* v, int64_t v_ld, int64_t v_bs, const int* step_ptr, int max_keys,
+                          const float* dec_bias, const int* lut, Planes ctx);
+void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
+                           int64_t kt_bs, const float* v, int64_t v_ld, int64_t v_bs, int n_keys, const int* mask,
+                           int mask_ld, Planes ctx);
+void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
+void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
+                          int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
+                          int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
+                          int64_t dump_ss);
+void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int B, int64_t* out_ids, int out_ld,
+                        int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x);
+
+void launch_out_len(cudaStream_t st, const int64_t* ids, int B, int ld, int ncols, int eos, int* len);
+
+}  // namespace mg

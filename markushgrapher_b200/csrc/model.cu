@@ -1,0 +1,995 @@
+// Host orchestration of the hot path and the model-level C ABI (mg_create ... mg_generate).
+// The layer loops below are the B200 replacement of
+//   * the fork's Markushgrapher encoder forward (Swin branch + projector + UdopStack encoder + fusion concat;
+//     stock restatement transformers/models/udop/modeling_udop.py:1064-1256, models/swin/modeling_swin.py:534-913),
+//   * GenerationMixin.generate / _sample (transformers/generation/utils.py:2131, 2658-2842) for greedy decode.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.h"
+#include "mg_b200.h"
+
+namespace mg {
+
+extern thread_local std::string g_last_error;
+int set_error(const Error& e);
+int set_error(const std::exception& e);
+
+static inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ memory
+// Chunked bump allocator: deterministic allocation sequences reuse the same addresses after reset().
+struct Arena {
+  struct Chunk {
+    char* base;
+    size_t cap, used;
+  };
+  std::vector<Chunk> chunks;
+  size_t chunk_bytes = (size_t)1 << 30;
+  size_t total = 0;
+  void* alloc(size_t bytes) {
+    bytes = (size_t)rup((int64_t)std::max<size_t>(bytes, 16), 1024);
+    for (auto& c : chunks) {
+      if (c.cap - c.used >= bytes) {
+        void* p = c.base + c.used;
+        c.used += bytes;
+        return p;
+      }
+    }
+    Chunk c;
+    c.cap = std::max(bytes, chunk_bytes);
+    MG_CHECK_CUDA(cudaMalloc((void**)&c.base, c.cap));
+    c.used = bytes;
+    total += c.cap;
+    chunks.push_back(c);
+    return c.base;
+  }
+  template <typename T>
+  T* get(int64_t n) {
+    return reinterpret_cast<T*>(alloc(sizeof(T) * (size_t)std::max<int64_t>(n, 1)));
+  }
+  void reset() {
+    for (auto& c : chunks) c.used = 0;
+  }
+  void release() {
+    for (auto& c : chunks) cudaFree(c.base);
+    chunks.clear();
+    total = 0;
+  }
+};
+
+struct RawWeight {
+  const float* ptr;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// a Linear layer repacked as split planes [N, ldk] (+ optional fp32 bias [N])
+struct LinearW {
+  Planes w;
+  int N = 0, K = 0;
+  int64_t ldk = 0;
+  const float* bias = nullptr;
+};
+
+struct EncLayer {
+  float *ln1, *ln2;
+  LinearW qk, v, o, wi, wo;
+};
+struct DecLayer {
+  float *ln1, *ln2, *ln3;
+  LinearW qkv, o, cq, ck, cv, co, wi, wo;
+};
+struct SwBlock {
+  float *ln1w, *ln1b, *ln2w, *ln2b, *table;
+  LinearW qkv, proj, fc1, fc2;
+};
+struct SwStage {
+  int C, heads, res;
+  std::vector<SwBlock> blocks;
+  bool has_down = false;
+  float *dnw = nullptr, *dnb = nullptr;
+  LinearW down;
+};
+
+}  // namespace mg
+
+using namespace mg;
+
+struct mg_model {
+  mg_config cfg;
+  bool finalized = false;
+  std::unordered_map<std::string, RawWeight> raw;
+  std::vector<void*> owned;
+  bool split2 = true;  // hi+lo planes
+
+  // weights
+  float* shared = nullptr;
+  LinearW patch_embed;
+  float *cell_x = nullptr, *cell_y = nullptr, *tab1d = nullptr, *tabh = nullptr, *tabv = nullptr;
+  std::vector<EncLayer> enc;
+  float* enc_final_ln = nullptr;
+  std::vector<DecLayer> dec;
+  float *dec_bias = nullptr, *dec_final_ln = nullptr;
+  LinearW lm_head;
+  LinearW sw_patch;
+  float *sw_emb_w = nullptr, *sw_emb_b = nullptr, *sw_ln_w = nullptr, *sw_ln_b = nullptr;
+  std::vector<SwStage> sw;
+  LinearW proj1, proj2;
+  int *lut_enc1d = nullptr, *lut_hv = nullptr, *lut_dec = nullptr;
+  int lut_enc1d_n = 0, lut_hv_n = 0, lut_dec_n = 0;
+
+  // derived
+  int NP = 0, np_side = 0, n_sw = 0, sw_dim = 0;
+
+  // run state
+  Arena persist, scratch;
+  int cur_B = 0, cur_Lt = 0, cur_S = 0, cur_Sp = 0, cur_M = 0, cur_Mp = 0;
+  float* mem = nullptr;   // [B, Mp, d]
+  Planes mem_pl;          // planes of mem
+  int* mem_mask = nullptr;  // [B, Mp]
+  int64_t launches = 0;
+  float last_encode_ms = 0.f, last_decode_ms = 0.f;
+  int64_t last_launches = 0;
+  int* pinned_flag = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t own_stream = nullptr;
+
+  ~mg_model() {
+    for (void* p : owned) cudaFree(p);
+    persist.release();
+    scratch.release();
+    if (pinned_flag) cudaFreeHost(pinned_flag);
+    if (own_stream) cudaStreamDestroy(own_stream);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+
+  // ---------------------------------------------------------------------------------------------- helpers
+  template <typename T>
+  T* own(int64_t n) {
+    void* p;
+    MG_CHECK_CUDA(cudaMalloc(&p, sizeof(T) * (size_t)std::max<int64_t>(n, 1)));
+    owned.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+  const RawWeight& need(const std::string& name) {
+    auto it = raw.find(name);
+    if (it == raw.end()) throw Error(-4, "missing weight: " + name);
+    return it->second;
+  }
+  float* copy_f32(cudaStream_t st, const std::string& name, int64_t expect_numel) {
+    const RawWeight& w = need(name);
+    MG_REQUIRE(w.numel() == expect_numel, "unexpected size for weight " + name);
+    float* p = own<float>(expect_numel);
+    MG_CHECK_CUDA(cudaMemcpyAsync(p, w.ptr, sizeof(float) * expect_numel, cudaMemcpyDeviceToDevice, st));
+    return p;
+  }
+  Planes new_planes_owned(int64_t n) {
+    Planes p;
+    p.hi = own<bf16>(n);
+    p.lo = split2 ? own<bf16>(n) : nullptr;
+    return p;
+  }
+  // Linear from one or more [n_i, K] weight matrices stacked along the output dim (+ stacked biases)
+  LinearW make_linear(cudaStream_t st, const std::vector<std::string>& wnames, const std::vector<std::string>& bnames,
+                      int K) {
+    LinearW L;
+    L.K = K;
+    L.ldk = rup(K, 8);
+    int N = 0;
+    for (auto& n : wnames) {
+      const RawWeight& w = need(n);
+      MG_REQUIRE(w.numel() % K == 0, "weight " + n + " is not [*, K]");
+      N += (int)(w.numel() / K);
+    }
+    L.N = N;
+    L.w = new_planes_owned((int64_t)N * L.ldk);
+    int row = 0;
+    for (auto& n : wnames) {
+      const RawWeight& w = need(n);
+      const int rows = (int)(w.numel() / K);
+      Planes dst{L.w.hi + (int64_t)row * L.ldk, L.w.lo ? L.w.lo + (int64_t)row * L.ldk : nullptr};
+      launch_split(st, w.ptr, rows, K, K, dst, L.ldk);
+      row += rows;
+    }
+    if (!bnames.empty()) {
+      float* b = own<float>(N);
+      int off = 0;
+      for (auto& n : bnames) {
+        const RawWeight& w = need(n);
+        MG_CHECK_CUDA(cudaMemcpyAsync(b + off, w.ptr, sizeof(float) * w.numel(), cudaMemcpyDeviceToDevice, st));
+        off += (int)w.numel();
+      }
+      MG_REQUIRE(off == N, "bias size mismatch for " + wnames[0]);
+      L.bias = b;
+    }
+    return L;
+  }
+  int* upload_lut(cudaStream_t st, const std::vector<int32_t>& v) {
+    int* p = own<int>((int64_t)v.size());
+    MG_CHECK_CUDA(cudaMemcpyAsync(p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, st));
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));  // v is a temporary
+    return p;
+  }
+
+  Planes planes(Arena& a, int64_t n) {
+    Planes p;
+    p.hi = a.get<bf16>(n);
+    p.lo = split2 ? a.get<bf16>(n) : nullptr;
+    return p;
+  }
+  static Planes offset(Planes p, int64_t off) { return Planes{p.hi + off, p.lo ? p.lo + off : nullptr}; }
+
+  // y[rows, N] = x[rows, K] * W^T  (x planes with row stride ldx)
+  void linear(cudaStream_t st, const LinearW& W, Planes x, int64_t ldx, int64_t rows, GemmEpilogue ep,
+              bool use_bias = true) {
+    GemmOperand A, B;
+    A.hi = x.hi; A.lo = x.lo; A.rows = rows; A.ld = ldx;
+    B.hi = W.w.hi; B.lo = W.w.lo; B.rows = W.N; B.ld = W.ldk;
+    if (use_bias && W.bias) ep.bias = W.bias;
+    if (ep.ld_r == 0) ep.ld_r = W.N;
+    launch_gemm(st, A, B, (int)rows, W.N, W.K, 1, 1, 1, ep, W.N <= 32 ? 32 : (W.N <= 64 ? 64 : 128));
+    ++launches;
+  }
+
+  void finalize(cudaStream_t st);
+  void encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
+              const int64_t* amask);
+  void swin_forward(cudaStream_t st, int B0, int Bc, const float* px);
+  void vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_t* ids, const float* bbox, const float* px,
+                   const int64_t* amask);
+  void generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len, float* step_logits,
+                int32_t* steps_run);
+};
+
+// ================================================================================================= finalize
+void mg_model::finalize(cudaStream_t st) {
+  const mg_config& c = cfg;
+  MG_REQUIRE(c.d_kv == 64 && c.num_heads * c.d_kv == c.d_model, "this build needs d_kv == 64 and heads*d_kv == d_model");
+  MG_REQUIRE(c.d_model % 128 == 0 && c.d_model <= 1024, "d_model must be a multiple of 128, <= 1024");
+  MG_REQUIRE(c.image_size % c.patch_size == 0, "image_size must be a multiple of patch_size");
+  split2 = c.precision == 0;
+  const int d = c.d_model, H = c.num_heads, V = c.vocab_size;
+  np_side = c.image_size / c.patch_size;
+  NP = np_side * np_side;
+
+  shared = copy_f32(st, "shared.weight", (int64_t)V * d);
+  patch_embed = make_linear(st, {"encoder.embed_patches.proj.weight"}, {"encoder.embed_patches.proj.bias"},
+                            3 * c.patch_size * c.patch_size);
+  cell_x = copy_f32(st, "encoder.cell_2d_embedding.x_position_embeddings.weight", (int64_t)c.max_2d * d);
+  cell_y = copy_f32(st, "encoder.cell_2d_embedding.y_position_embeddings.weight", (int64_t)c.max_2d * d);
+  tab1d = copy_f32(st, "encoder.relative_bias.biases.0.relative_attention_bias.weight", (int64_t)c.rel_buckets * H);
+  tabh = copy_f32(st, "encoder.relative_bias.biases.1.relative_attention_bias.weight", (int64_t)c.rel_buckets * H);
+  tabv = copy_f32(st, "encoder.relative_bias.biases.2.relative_attention_bias.weight", (int64_t)c.rel_buckets * H);
+  enc.resize(c.num_layers);
+  for (int i = 0; i < c.num_layers; ++i) {
+    const std::string p = "encoder.block." + std::to_string(i) + ".layer.";
+    EncLayer& L = enc[i];
+    L.ln1 = copy_f32(st, p + "0.layer_norm.weight", d);
+    L.qk = make_linear(st, {p + "0.SelfAttention.q.weight", p + "0.SelfAttention.k.weight"}, {}, d);
+    L.v = make_linear(st, {p + "0.SelfAttention.v.weight"}, {}, d);
+    L.o = make_linear(st, {p + "0.SelfAttention.o.weight"}, {}, d);
+    L.ln2 = copy_f32(st, p + "1.layer_norm.weight", d);
+    L.wi = make_linear(st, {p + "1.DenseReluDense.wi.weight"}, {}, d);
+    L.wo = make_linear(st, {p + "1.DenseReluDense.wo.weight"}, {}, c.d_ff);
+  }
+  enc_final_ln = copy_f32(st, "encoder.final_layer_norm.weight", d);
+  dec.resize(c.num_decoder_layers);
+  for (int i = 0; i < c.num_decoder_layers; ++i) {
+    const std::string p = "decoder.block." + std::to_string(i) + ".layer.";
+    DecLayer& L = dec[i];
+    L.ln1 = copy_f32(st, p + "0.layer_norm.weight", d);
+    L.qkv = make_linear(st, {p + "0.SelfAttention.q.weight", p + "0.SelfAttention.k.weight", p + "0.SelfAttention.v.weight"}, {}, d);
+    L.o = make_linear(st, {p + "0.SelfAttention.o.weight"}, {}, d);
+    L.ln2 = copy_f32(st, p + "1.layer_norm.weight", d);
+    L.cq = make_linear(st, {p + "1.EncDecAttention.q.weight"}, {}, d);
+    L.ck = make_linear(st, {p + "1.EncDecAttention.k.weight"}, {}, d);
+    L.cv = make_linear(st, {p + "1.EncDecAttention.v.weight"}, {}, d);
+    L.co = make_linear(st, {p + "1.EncDecAttention.o.weight"}, {}, d);
+    L.ln3 = copy_f32(st, p + "2.layer_norm.weight", d);
+    L.wi = make_linear(st, {p + "2.DenseReluDense.wi.weight"}, {}, d);
+    L.wo = make_linear(st, {p + "2.DenseReluDense.wo.weight"}, {}, c.d_ff);
+  }
+  dec_bias = copy_f32(st, "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", (int64_t)c.rel_buckets * H);
+  dec_final_ln = copy_f32(st, "decoder.final_layer_norm.weight", d);
+  lm_head = make_linear(st, {"lm_head.weight"}, {}, d);
+
+  // ---- Swin
+  const std::string sp = "encoder.molscribe_encoder.";
+  MG_REQUIRE(c.swin_num_stages >= 1 && c.swin_num_stages <= MG_MAX_SWIN_STAGES, "bad swin_num_stages");
+  MG_REQUIRE(c.swin_image % c.swin_patch == 0, "swin image must be a multiple of its patch size");
+  sw_patch = make_linear(st, {sp + "embeddings.patch_embeddings.projection.weight"},
+                         {sp + "embeddings.patch_embeddings.projection.bias"}, 3 * c.swin_patch * c.swin_patch);
+  sw_emb_w = copy_f32(st, sp + "embeddings.norm.weight", c.swin_embed);
+  sw_emb_b = copy_f32(st, sp + "embeddings.norm.bias", c.swin_embed);
+  sw.resize(c.swin_num_stages);
+  int res = c.swin_image / c.swin_patch;
+  int C = c.swin_embed;
+  const int ntab = (2 * c.swin_window - 1) * (2 * c.swin_window - 1);
+  for (int s = 0; s < c.swin_num_stages; ++s) {
+    SwStage& S = sw[s];
+    S.C = C;
+    S.heads = c.swin_heads[s];
+    S.res = res;
+    MG_REQUIRE(C / S.heads == 32 && C % S.heads == 0, "Swin head_dim must be 32");
+    MG_REQUIRE(res % std::min(res, c.swin_window) == 0 && res >= c.swin_window,
+               "Swin stage resolution must be a multiple of (and at least) the window size");
+    S.blocks.resize(c.swin_depths[s]);
+    for (int b = 0; b < c.swin_depths[s]; ++b) {
+      const std::string p = sp + "encoder.layers." + std::to_string(s) + ".blocks." + std::to_string(b) + ".";
+      SwBlock& K = S.blocks[b];
+      K.ln1w = copy_f32(st, p + "layernorm_before.weight", C);
+      K.ln1b = copy_f32(st, p + "layernorm_before.bias", C);
+      K.qkv = make_linear(st, {p + "attention.self.query.weight", p + "attention.self.key.weight", p + "attention.self.value.weight"},
+                          {p + "attention.self.query.bias", p + "attention.self.key.bias", p + "attention.self.value.bias"}, C);
+      K.table = copy_f32(st, p + "attention.self.relative_position_bias_table", (int64_t)ntab * S.heads);
+      K.proj = make_linear(st, {p + "attention.output.dense.weight"}, {p + "attention.output.dense.bias"}, C);
+      K.ln2w = copy_f32(st, p + "layernorm_after.weight", C);
+      K.ln2b = copy_f32(st, p + "layernorm_after.bias", C);
+      K.fc1 = make_linear(st, {p + "intermediate.dense.weight"}, {p + "intermediate.dense.bias"}, C);
+      K.fc2 = make_linear(st, {p + "output.dense.weight"}, {p + "output.dense.bias"}, 4 * C);
+    }
+    if (s + 1 < c.swin_num_stages) {
+      const std::string p = sp + "encoder.layers." + std::to_string(s) + ".downsample.";
+      S.has_down = true;
+      S.dnw = copy_f32(st, p + "norm.weight", 4 * C);
+      S.dnb = copy_f32(st, p + "norm.bias", 4 * C);
+      S.down = make_linear(st, {p + "reduction.weight"}, {}, 4 * C);
+      MG_REQUIRE(res % 2 == 0, "Swin stage resolution must be even for patch merging");
+      res /= 2;
+      C *= 2;
+    }
+  }
+  sw_dim = C;
+  n_sw = res * res;
+  sw_ln_w = copy_f32(st, sp + "layernorm.weight", C);
+  sw_ln_b = copy_f32(st, sp + "layernorm.bias", C);
+  proj1 = make_linear(st, {"encoder.molscribe_projector.0.weight"}, {"encoder.molscribe_projector.0.bias"}, C);
+  proj2 = make_linear(st, {"encoder.molscribe_projector.2.weight"}, {"encoder.molscribe_projector.2.bias"}, c.proj_hidden);
+  MG_REQUIRE(proj1.N == c.proj_hidden && proj2.N == d, "projector shapes do not match the config");
+
+  // ---- integer LUTs of the bucket functions
+  {
+    std::vector<int32_t> l(c.rel_max_distance + 1);
+    rel_bucket_lut(1, c.rel_buckets, c.rel_max_distance, (int)l.size(), l.data());
+    lut_enc1d = upload_lut(st, l);
+    lut_enc1d_n = (int)l.size();
+    std::vector<int32_t> lh(101);
+    rel_bucket_lut(1, c.rel_buckets, 100, (int)lh.size(), lh.data());  // RelativePositionBiasHorizontal/Vertical: max_distance 100
+    lut_hv = upload_lut(st, lh);
+    lut_hv_n = (int)lh.size();
+    std::vector<int32_t> ld(c.rel_max_distance + 1);
+    rel_bucket_lut(0, c.rel_buckets, c.rel_max_distance, (int)ld.size(), ld.data());
+    // the decode kernel indexes lut[step - j] directly: extend to any distance by clamping on the host
+    std::vector<int32_t> ldx(4096);
+    for (int i = 0; i < 4096; ++i) ldx[i] = ld[std::min<int>(i, c.rel_max_distance)];
+    lut_dec = upload_lut(st, ldx);
+    lut_dec_n = 4096;
+  }
+  MG_CHECK_CUDA(cudaMallocHost((void**)&pinned_flag, 64));
+  for (auto& e : ev) MG_CHECK_CUDA(cudaEventCreate(&e));
+  MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  raw.clear();
+  finalized = true;
+}
+
+// ================================================================================================= Swin branch
+void mg_model::swin_forward(cudaStream_t st, int B0, int Bc, const float* px_all) {
+  const mg_config& c = cfg;
+  Arena& a = scratch;
+  const int d = c.d_model;
+  const float* px = px_all + (int64_t)B0 * 3 * c.image_size * c.image_size;
+  const int SI = c.swin_image;
+  if (c.image_size != SI) {
+    float* rs = a.get<float>((int64_t)Bc * 3 * SI * SI);
+    launch_resize_bilinear(st, px, Bc, c.image_size, c.image_size, SI, SI, rs);
+    ++launches;
+    px = rs;
+  }
+  int res = SI / c.swin_patch;
+  int64_t T = (int64_t)Bc * res * res;
+  // patch embedding + LayerNorm
+  Planes col = planes(a, T * sw_patch.ldk);
+  launch_im2col(st, px, Bc, SI, SI, c.swin_patch, (int)sw_patch.ldk, col);
+  ++launches;
+  float* pe = a.get<float>(T * c.swin_embed);
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = pe;
+    linear(st, sw_patch, col, sw_patch.ldk, T, ep);
+  }
+  float* x = a.get<float>(T * c.swin_embed);
+  launch_layernorm_any(st, pe, nullptr, 1, c.swin_embed, T, sw_emb_w, sw_emb_b, c.swin_ln_eps, Planes{}, x);
+  ++launches;
+
+  for (size_t s = 0; s < sw.size(); ++s) {
+    SwStage& S = sw[s];
+    const int C = S.C;
+    res = S.res;
+    T = (int64_t)Bc * res * res;
+    const int ws = std::min(c.swin_window, res);
+    int* map0 = a.get<int>(T);
+    int* map1 = a.get<int>(T);
+    launch_window_rowmap(st, Bc, res, res, ws, 0, map0);
+    ++launches;
+    const bool can_shift = res > c.swin_window;
+    if (can_shift) {
+      launch_window_rowmap(st, Bc, res, res, ws, ws / 2, map1);
+      ++launches;
+    }
+    Planes xw = planes(a, T * C);
+    float* qkv = a.get<float>(T * 3 * C);
+    Planes ctx = planes(a, T * C);
+    Planes hid = planes(a, T * 4 * C);
+    for (size_t b = 0; b < S.blocks.size(); ++b) {
+      SwBlock& K = S.blocks[b];
+      const int shift = (b % 2 == 1 && can_shift) ? ws / 2 : 0;
+      const int* map = shift ? map1 : map0;
+      launch_layernorm_any(st, x, map, 1, C, T, K.ln1w, K.ln1b, c.swin_ln_eps, xw, nullptr);
+      ++launches;
+      {
+        GemmEpilogue ep;
+        ep.out_f32 = qkv;
+        linear(st, K.qkv, xw, C, T, ep);
+      }
+      launch_window_attn(st, qkv, K.table, T / (ws * ws), C, S.heads, ws, res, res, shift, ctx);
+      ++launches;
+      {
+        GemmEpilogue ep;  // proj + bias, scattered back to spatial order and added to the shortcut (in place)
+        ep.out_f32 = x;
+        ep.residual = x;
+        ep.row_map = map;
+        ep.ld_r = C;
+        linear(st, K.proj, ctx, C, T, ep);
+      }
+      launch_layernorm_any(st, x, nullptr, 1, C, T, K.ln2w, K.ln2b, c.swin_ln_eps, xw, nullptr);
+      ++launches;
+      {
+        GemmEpilogue ep;
+        ep.out_hi = hid.hi;
+        ep.out_lo = hid.lo;
+        ep.act = ACT_GELU_ERF;
+        linear(st, K.fc1, xw, C, T, ep);
+      }
+      {
+        GemmEpilogue ep;
+        ep.out_f32 = x;
+        ep.residual = x;
+        linear(st, K.fc2, hid, 4 * C, T, ep);
+      }
+    }
+    if (S.has_down) {
+      const int64_t T2 = T / 4;
+      int* mm = a.get<int>(T2 * 4);
+      launch_merge_rowmap(st, Bc, res, res, mm);
+      ++launches;
+      Planes mg4 = planes(a, T2 * 4 * C);
+      launch_layernorm_any(st, x, mm, 4, C, T2, S.dnw, S.dnb, c.swin_ln_eps, mg4, nullptr);
+      ++launches;
+      float* xn = a.get<float>(T2 * 2 * C);
+      GemmEpilogue ep;
+      ep.out_f32 = xn;
+      linear(st, S.down, mg4, 4 * C, T2, ep);
+      x = xn;
+    }
+  }
+  // final LayerNorm -> projector -> e1 rows [0, n_sw) of the encoder memory
+  const int64_t Tn = (int64_t)Bc * n_sw;
+  Planes f = planes(a, Tn * sw_dim);
+  launch_layernorm_any(st, x, nullptr, 1, sw_dim, Tn, sw_ln_w, sw_ln_b, c.swin_ln_eps, f, nullptr);
+  ++launches;
+  Planes ph = planes(a, Tn * c.proj_hidden);
+  {
+    GemmEpilogue ep;
+    ep.out_hi = ph.hi;
+    ep.out_lo = ph.lo;
+    ep.act = ACT_GELU_ERF;
+    linear(st, proj1, f, sw_dim, Tn, ep);
+  }
+  {
+    GemmOperand A, Bop;
+    A.hi = ph.hi; A.lo = ph.lo; A.rows = n_sw; A.ld = c.proj_hidden; A.use_b2 = true; A.bs2 = (int64_t)n_sw * c.proj_hidden;
+    Bop.hi = proj2.w.hi; Bop.lo = proj2.w.lo; Bop.rows = proj2.N; Bop.ld = proj2.ldk;
+    GemmEpilogue ep;
+    ep.out_f32 = mem + (int64_t)B0 * cur_Mp * d;
+    ep.ld_r = d;
+    ep.bs2 = (int64_t)cur_Mp * d;
+    ep.bias = proj2.bias;
+    launch_gemm(st, A, Bop, n_sw, d, c.proj_hidden, 1, Bc, 1, ep, 128);
+    ++launches;
+  }
+}
+
+// ================================================================================================= VTL encoder
+void mg_model::vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_t* ids, const float* bbox,
+                           const float* px_all, const int64_t* amask) {
+  const mg_config& c = cfg;
+  Arena& a = scratch;
+  const int d = c.d_model, H = c.num_heads, Sp = cur_Sp, S = cur_S;
+  const float* px = px_all + (int64_t)B0 * 3 * c.image_size * c.image_size;
+  ids += (int64_t)B0 * Lt;
+  bbox += (int64_t)B0 * Lt * 4;
+  if (amask) amask += (int64_t)B0 * Lt;
+  const int64_t T = (int64_t)Bc * Sp;
+
+  // patch embeddings (Conv2d k16 s16 == GEMM over im2col rows)
+  Planes col = planes(a, (int64_t)Bc * NP * patch_embed.ldk);
+  launch_im2col(st, px, Bc, c.image_size, c.image_size, c.patch_size, (int)patch_embed.ldk, col);
+  ++launches;
+  float* pemb = a.get<float>((int64_t)Bc * NP * d);
+  {
+    GemmEpilogue ep;
+    ep.out_f32 = pemb;
+    linear(st, patch_embed, col, patch_embed.ldk, (int64_t)Bc * NP, ep);
+  }
+  // token/patch fusion + compaction + cell embeddings
+  float* x = a.get<float>(T * d);
+  double* bbox_ext = a.get<double>(T * 4);
+  int* vmask = a.get<int>(T);
+  int* ocr_pt = a.get<int>((int64_t)Bc * Lt);
+  int* vis_src = a.get<int>((int64_t)Bc * NP);
+  int* n_vis = a.get<int>(Bc);
+  launch_combine(st, ids, bbox, amask, shared, pemb, cell_x, cell_y, Bc, Lt, np_side, Sp, d, c.max_2d, c.vocab_size,
+                 ocr_pt, vis_src, n_vis, x, bbox_ext, vmask);
+  launches += 2;
+  uchar2* hv = a.get<uchar2>(T * Sp);
+  launch_relbucket_hv(st, bbox_ext, Bc, Sp, lut_hv, lut_hv_n, c.rel_buckets / 2, hv);
+  ++launches;
+
+  Planes xn = planes(a, T * d);
+  Planes qk = planes(a, T * 2 * d);
+  Planes vt = planes(a, T * d);  // [Bc][d][Sp]
+  float* scores = a.get<float>((int64_t)Bc * H * Sp * Sp);
+  Planes P = planes(a, (int64_t)Bc * H * Sp * Sp);
+  Planes ctx = planes(a, T * d);
+  Planes hid = planes(a, T * c.d_ff);
+
+  for (int l = 0; l < c.num_layers; ++l) {
+    EncLayer& L = enc[l];
+    launch_rmsnorm(st, x, L.ln1, T, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
+    ++launches;
+    {
+      GemmEpilogue ep;
+      ep.out_hi = qk.hi;
+      ep.out_lo = qk.lo;
+      linear(st, L.qk, xn, d, T, ep);
+    }
+    {  // V^T per image: vt[b][feature][token] = Wv . xn[b]^T
+      GemmOperand A, Bop;
+      A.hi = L.v.w.hi; A.lo = L.v.w.lo; A.rows = d; A.ld = L.v.ldk;
+      Bop.hi = xn.hi; Bop.lo = xn.lo; Bop.rows = Sp; Bop.ld = d; Bop.use_b2 = true; Bop.bs2 = (int64_t)Sp * d;
+      GemmEpilogue ep;
+      ep.out_hi = vt.hi;
+      ep.out_lo = vt.lo;
+      ep.ld_r = Sp;
+      ep.bs2 = (int64_t)d * Sp;
+      launch_gemm(st, A, Bop, d, Sp, d, 1, Bc, 1, ep, 128);
+      ++launches;
+    }
+    {  // scores[b][h] = q k^T   (no 1/sqrt(d) scaling in T5)
+      GemmOperand A, Bop;
+      A.hi = qk.hi; A.lo = qk.lo; A.rows = Sp; A.ld = 2 * d;
+      A.use_b1 = true; A.bs1 = 64; A.use_b2 = true; A.bs2 = (int64_t)Sp * 2 * d;
+      Bop = A;
+      Bop.hi = qk.hi + d;
+      Bop.lo = qk.lo ? qk.lo + d : nullptr;
+      GemmEpilogue ep;
+      ep.out_f32 = scores;
+      ep.ld_r = Sp;
+      ep.bs1 = (int64_t)Sp * Sp;
+      ep.bs2 = (int64_t)H * Sp * Sp;
+      launch_gemm(st, A, Bop, Sp, Sp, 64, H, Bc, 1, ep, 128);
+      ++launches;
+    }
+    launch_enc_softmax(st, scores, hv, vmask, tab1d, tabh, tabv, lut_enc1d, lut_enc1d_n, c.rel_buckets / 2,
+                       c.rel_buckets, Bc, H, Sp, P);
+    ++launches;
+    {  // ctx[b][:, h*64:(h+1)*64] = P[b][h] . V[b][h]
+      GemmOperand A, Bop;
+      A.hi = P.hi; A.lo = P.lo; A.rows = Sp; A.ld = Sp;
+      A.use_b1 = true; A.bs1 = (int64_t)Sp * Sp; A.use_b2 = true; A.bs2 = (int64_t)H * Sp * Sp;
+      Bop.hi = vt.hi; Bop.lo = vt.lo; Bop.rows = 64; Bop.ld = Sp;
+      Bop.use_b1 = true; Bop.bs1 = (int64_t)64 * Sp; Bop.use_b2 = true; Bop.bs2 = (int64_t)d * Sp;
+      GemmEpilogue ep;
+      ep.out_hi = ctx.hi;
+      ep.out_lo = ctx.lo;
+      ep.ld_r = d;
+      ep.bs1 = 64;
+      ep.bs2 = (int64_t)Sp * d;
+      launch_gemm(st, A, Bop, Sp, 64, Sp, H, Bc, 1, ep, 64);
+      ++launches;
+    }
+    {
+      GemmEpilogue ep;
+      ep.out_f32 = x;
+      ep.residual = x;
+      linear(st, L.o, ctx, d, T, ep);
+    }
+    launch_rmsnorm(st, x, L.ln2, T, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
+    ++launches;
+    {
+      GemmEpilogue ep;
+      ep.out_hi = hid.hi;
+      ep.out_lo = hid.lo;
+      ep.act = ACT_RELU;
+      linear(st, L.wi, xn, d, T, ep);
+    }
+    {
+      GemmEpilogue ep;
+      ep.out_f32 = x;
+      ep.residual = x;
+      linear(st, L.wo, hid, c.d_ff, T, ep);
+    }
+  }
+  // final RMSNorm straight into rows [n_sw, n_sw+Sp) of the encoder memory
+  launch_rmsnorm(st, x, enc_final_ln, T, d, c.ln_eps, 1.f, Planes{}, mem + (int64_t)B0 * cur_Mp * d, Sp,
+                 (int64_t)cur_Mp * d, (int64_t)n_sw * d);
+  ++launches;
+  launch_build_mem_mask(st, vmask, Bc, Sp, S, n_sw, cur_Mp, mem_mask + (int64_t)B0 * cur_Mp);
+  ++launches;
+  (void)S;
+}
+
+void mg_model::encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
+                      const int64_t* amask) {
+  MG_REQUIRE(finalized, "mg_finalize has not been called");
+  MG_REQUIRE(B > 0 && Lt > 0, "empty batch");
+  const mg_config& c = cfg;
+  const int d = c.d_model;
+  cur_B = B;
+  cur_Lt = Lt;
+  cur_S = Lt + NP;
+  cur_Sp = (int)rup(cur_S, 8);
+  cur_M = n_sw + cur_S;
+  cur_Mp = (int)rup(n_sw + cur_Sp, 8);
+  persist.reset();
+  mem = persist.get<float>((int64_t)B * cur_Mp * d);
+  mem_pl = planes(persist, (int64_t)B * cur_Mp * d);
+  mem_mask = persist.get<int>((int64_t)B * cur_Mp);
+  MG_CHECK_CUDA(cudaMemsetAsync(mem, 0, sizeof(float) * (int64_t)B * cur_Mp * d, st));
+  const int chunk = c.enc_chunk > 0 ? c.enc_chunk : 64;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bc = std::min(chunk, B - b0);
+    scratch.reset();
+    swin_forward(st, b0, bc, px);
+    scratch.reset();
+    vtl_forward(st, b0, bc, Lt, ids, bbox, px, amask);
+  }
+  launch_split(st, mem, (int64_t)B * cur_Mp, d, d, mem_pl, d);
+  ++launches;
+}
+
+// ================================================================================================= greedy decode
+void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len,
+                        float* step_logits, int32_t* steps_run) {
+  const mg_config& c = cfg;
+  MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
+  MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
+  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
+  Arena& a = scratch;
+  a.reset();
+  const int Tp = (int)rup(max_length, 4);
+  const int64_t Vld = rup(V, 4);
+
+  // ---- cross K^T / V for every layer (once per generate; UdopAttention :575-583)
+  std::vector<float*> ckt(NL), cv(NL);
+  for (int l = 0; l < NL; ++l) {
+    ckt[l] = a.get<float>((int64_t)B * d * Mp);
+    cv[l] = a.get<float>((int64_t)B * Mp * d);
+    {
+      GemmOperand A, Bop;
+      A.hi = dec[l].ck.w.hi; A.lo = dec[l].ck.w.lo; A.rows = d; A.ld = dec[l].ck.ldk;
+      Bop.hi = mem_pl.hi; Bop.lo = mem_pl.lo; Bop.rows = Mp; Bop.ld = d; Bop.use_b2 = true; Bop.bs2 = (int64_t)Mp * d;
+      GemmEpilogue ep;
+      ep.out_f32 = ckt[l];
+      ep.ld_r = Mp;
+      ep.bs2 = (int64_t)d * Mp;
+      launch_gemm(st, A, Bop, d, Mp, d, 1, B, 1, ep, 128);
+      ++launches;
+    }
+    {
+      GemmEpilogue ep;
+      ep.out_f32 = cv[l];
+      linear(st, dec[l].cv, mem_pl, d, (int64_t)B * Mp, ep);
+    }
+  }
+  // ---- decode state
+  std::vector<float*> skt(NL), sv(NL);
+  for (int l = 0; l < NL; ++l) {
+    skt[l] = a.get<float>((int64_t)B * d * Tp);
+    sv[l] = a.get<float>((int64_t)B * Tp * d);
+  }
+  float* x = a.get<float>((int64_t)B * d);
+  Planes xn = planes(a, (int64_t)B * d);
+  float* qkv = a.get<float>((int64_t)B * 3 * d);
+  float* q = a.get<float>((int64_t)B * d);
+  Planes ctx = planes(a, (int64_t)B * d);
+  float* hbuf = a.get<float>((int64_t)B * c.d_ff);
+  Planes hpl = planes(a, (int64_t)B * c.d_ff);
+  float* logits = a.get<float>((int64_t)B * Vld);
+  int* finished = a.get<int>(B);
+  int* ctr = a.get<int>(8);  // [0]=step [1]=n_unfinished [2]=ticket
+  int64_t* ids_dev = out_ids;
+  launch_decode_init(st, shared, d, c.decoder_start_token_id, B, ids_dev, max_length, finished, ctr, ctr + 1, ctr + 2, x);
+  ++launches;
+
+  const int bn = B <= 32 ? 32 : (B <= 64 ? 64 : 128);
+  const int nbt = (B + bn - 1) / bn;
+  // skinny GEMM: out[b][n] += sum_k W[n][k] act[b][k], W rows on the MMA M axis, split-K over CTAs
+  auto skinny = [&](const LinearW& W, Planes act, float* out, int64_t out_ld, bool zero_first) {
+    if (zero_first) MG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * out_ld, st));
+    GemmOperand A, Bop;
+    A.hi = W.w.hi; A.lo = W.w.lo; A.rows = W.N; A.ld = W.ldk;
+    Bop.hi = act.hi; Bop.lo = act.lo; Bop.rows = B; Bop.ld = W.K;
+    GemmEpilogue ep;
+    ep.out_f32 = out;
+    ep.ld_r = 1;
+    ep.ld_c = out_ld;
+    ep.atomic = 1;
+    const int tiles = ((W.N + 127) / 128) * nbt;
+    int ks = std::max(1, 148 / tiles);
+    launch_gemm(st, A, Bop, W.N, B, W.K, 1, 1, ks, ep, bn);
+    ++launches;
+  };
+  auto one_step = [&]() {
+    for (int l = 0; l < NL; ++l) {
+      DecLayer& L = dec[l];
+      launch_rmsnorm(st, x, L.ln1, B, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
+      skinny(L.qkv, xn, qkv, 3 * d, true);
+      launch_dec_self_attn(st, qkv, B, H, d, skt[l], Tp, (int64_t)d * Tp, sv[l], d, (int64_t)Tp * d, ctr, Tp, dec_bias,
+                           lut_dec, ctx);
+      skinny(L.o, ctx, x, d, false);  // x += o(ctx)
+      launch_rmsnorm(st, x, L.ln2, B, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
+      skinny(L.cq, xn, q, d, true);
+      launch_dec_cross_attn(st, q, B, H, d, ckt[l], Mp, (int64_t)d * Mp, cv[l], d, (int64_t)Mp * d, Mp, mem_mask, Mp,
+                            ctx);
+      skinny(L.co, ctx, x, d, false);
+      launch_rmsnorm(st, x, L.ln3, B, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
+      skinny(L.wi, xn, hbuf, c.d_ff, true);
+      launch_relu_split(st, hbuf, (int64_t)B * c.d_ff, hpl);
+      skinny(L.wo, hpl, x, d, false);
+      launches += 6;
+    }
+    launch_rmsnorm(st, x, dec_final_ln, B, d, c.ln_eps, c.logit_scale, xn, nullptr, 0, 0, 0);
+    {
+      GemmOperand A, Bop;
+      A.hi = lm_head.w.hi; A.lo = lm_head.w.lo; A.rows = V; A.ld = lm_head.ldk;
+      Bop.hi = xn.hi; Bop.lo = xn.lo; Bop.rows = B; Bop.ld = d;
+      GemmEpilogue ep;
+      ep.out_f32 = logits;
+      ep.ld_r = 1;
+      ep.ld_c = Vld;
+      launch_gemm(st, A, Bop, V, B, d, 1, 1, 1, ep, bn);
+    }
+    launch_greedy_select(st, logits, B, V, Vld, shared, d, c.eos_token_id, c.pad_token_id, ids_dev, max_length,
+                         finished, ctr, ctr + 1, ctr + 2, x, step_logits, (int64_t)(max_length - 1) * V, V);
+    launches += 3;
+  };
+
+  const int total_steps = max_length - 1;
+  int done_steps = 0;
+  // step 0 runs eagerly (lazy one-time initialisation happens outside graph capture) ...
+  one_step();
+  done_steps = 1;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  const int64_t per_step = launches;
+  if (total_steps > 1) {
+    // ... then one step is captured and replayed; every kernel reads the step index from device memory
+    const int64_t before = launches;
+    MG_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      one_step();
+    } catch (...) {
+      cudaGraph_t g2;
+      cudaStreamEndCapture(st, &g2);
+      throw;
+    }
+    MG_CHECK_CUDA(cudaStreamEndCapture(st, &graph));
+    MG_CHECK_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    const int64_t step_launches = launches - before;
+    launches = before;
+    pinned_flag[0] = B;
+    const int check_every = 16;
+    bool stop = false;
+    while (done_steps < total_steps && !stop) {
+      const int n = std::min(check_every, total_steps - done_steps);
+      for (int i = 0; i < n; ++i) MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+      launches += step_launches * n;
+      done_steps += n;
+      // poll the "all finished" counter one window late so the GPU never drains
+      MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));
+      if (pinned_flag[0] == 0) stop = true;
+      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
+    }
+  }
+  (void)per_step;
+  if (out_len) {
+    launch_out_len(st, ids_dev, B, max_length, std::min(done_steps + 1, max_length), c.eos_token_id, out_len);
+    ++launches;
+  }
+  MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  if (steps_run) *steps_run = done_steps;
+}
+
+// ================================================================================================= C ABI
+#define MG_API_BEGIN try {
+#define MG_API_END                                        \
+  return 0;                                               \
+  }                                                       \
+  catch (const mg::Error& e) { return mg::set_error(e); } \
+  catch (const std::exception& e) { return mg::set_error(e); }
+
+extern "C" {
+
+int mg_device_available(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n > 0 ? 1 : 0;
+}
+
+int mg_rel_bucket_lut(int bidirectional, int num_buckets, int max_distance, int n_entries, int32_t* lut_host) {
+  MG_API_BEGIN
+  MG_REQUIRE(lut_host && n_entries > 0 && num_buckets >= 4, "bad arguments");
+  rel_bucket_lut(bidirectional, num_buckets, max_distance, n_entries, lut_host);
+  MG_API_END
+}
+
+int mg_create(const mg_config* cfg, mg_model** out) {
+  MG_API_BEGIN
+  MG_REQUIRE(cfg && out, "null argument");
+  mg_model* m = new mg_model();
+  m->cfg = *cfg;
+  *out = m;
+  MG_API_END
+}
+
+void mg_destroy(mg_model* m) { delete m; }
+
+int mg_load_weight(mg_model* m, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int rank) {
+  try {
+    MG_REQUIRE(m && name && dev_ptr && rank >= 0 && rank <= 8, "bad arguments");
+    MG_REQUIRE(dtype == 0, "only fp32 weights are accepted");
+    MG_REQUIRE(!m->finalized, "model already finalized");
+    RawWeight w;
+    w.ptr = static_cast<const float*>(dev_ptr);
+    w.shape.assign(shape, shape + rank);
+    m->raw[name] = w;
+    return 0;
+  } catch (const mg::Error& e) {
+    return mg::set_error(e);
+  } catch (const std::exception& e) {
+    return mg::set_error(e);
+  }
+}
+
+int mg_finalize(mg_model* m, void* stream) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  m->finalize(static_cast<cudaStream_t>(stream));
+  MG_API_END
+}
+
+int mg_encode(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+              const float* pixel_values, const int64_t* attn_mask, float* enc_out, int32_t* enc_mask, int32_t* M_out) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
+  const int d = m->cfg.d_model, M = m->cur_M, Mp = m->cur_Mp;
+  if (enc_out)
+    MG_CHECK_CUDA(cudaMemcpy2DAsync(enc_out, sizeof(float) * (size_t)M * d, m->mem, sizeof(float) * (size_t)Mp * d,
+                                    sizeof(float) * (size_t)M * d, B, cudaMemcpyDeviceToDevice, st));
+  if (enc_mask)
+    MG_CHECK_CUDA(cudaMemcpy2DAsync(enc_mask, sizeof(int) * (size_t)M, m->mem_mask, sizeof(int) * (size_t)Mp,
+                                    sizeof(int) * (size_t)M, B, cudaMemcpyDeviceToDevice, st));
+  if (M_out) *M_out = M;
+  MG_API_END
+}
+
+int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length, int64_t* out_ids,
+                int32_t* out_len, float* step_logits, int32_t* steps_run) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values && out_ids, "null argument");
+  MG_REQUIRE(num_beams == 1, "beam search is not implemented in this revision (num_beams must be 1)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr || st == cudaStreamLegacy) {
+    // the decode step is replayed from a captured CUDA graph and the legacy default stream cannot be
+    // captured: run on the model's own stream, ordered after everything already queued on the device
+    MG_CHECK_CUDA(cudaDeviceSynchronize());
+    if (!m->own_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    st = m->own_stream;
+  }
+  const int64_t l0 = m->launches;
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[0], st));
+  m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[1], st));
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[3], st));
+  m->generate(st, B, max_length, out_ids, out_len, step_logits, steps_run);
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[2], st));
+  MG_CHECK_CUDA(cudaEventSynchronize(m->ev[2]));
+  MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_encode_ms, m->ev[0], m->ev[1]));
+  MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_decode_ms, m->ev[1], m->ev[2]));
+  m->last_launches = m->launches - l0;
+  MG_API_END
+}
+
+int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                     const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length,
+                     int64_t* out_ids, int32_t* out_len, int32_t* steps_run) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values && out_ids, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr || st == cudaStreamLegacy) {
+    MG_CHECK_CUDA(cudaDeviceSynchronize());
+    if (!m->own_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    st = m->own_stream;
+  }
+  const mg_config& c = m->cfg;
+  // staging buffers live in their own small allocations (kept across calls)
+  static thread_local void* stage = nullptr;
+  static thread_local size_t stage_cap = 0;
+  const size_t n_ids = (size_t)B * Lt, n_px = (size_t)B * 3 * c.image_size * c.image_size;
+  const size_t need = rup(n_ids * 8, 256) * 2 + rup(n_ids * 16, 256) + rup(n_px * 4, 256) + rup((size_t)B * max_length * 8, 256);
+  if (need > stage_cap) {
+    if (stage) cudaFree(stage);
+    MG_CHECK_CUDA(cudaMalloc(&stage, need));
+    stage_cap = need;
+  }
+  char* p = static_cast<char*>(stage);
+  int64_t* d_ids = reinterpret_cast<int64_t*>(p); p += rup(n_ids * 8, 256);
+  int64_t* d_mask = reinterpret_cast<int64_t*>(p); p += rup(n_ids * 8, 256);
+  float* d_box = reinterpret_cast<float*>(p); p += rup(n_ids * 16, 256);
+  float* d_px = reinterpret_cast<float*>(p); p += rup(n_px * 4, 256);
+  int64_t* d_out = reinterpret_cast<int64_t*>(p);
+  MG_CHECK_CUDA(cudaMemcpyAsync(d_ids, input_ids, n_ids * 8, cudaMemcpyHostToDevice, st));
+  if (attn_mask) MG_CHECK_CUDA(cudaMemcpyAsync(d_mask, attn_mask, n_ids * 8, cudaMemcpyHostToDevice, st));
+  MG_CHECK_CUDA(cudaMemcpyAsync(d_box, bbox, n_ids * 16, cudaMemcpyHostToDevice, st));
+  MG_CHECK_CUDA(cudaMemcpyAsync(d_px, pixel_values, n_px * 4, cudaMemcpyHostToDevice, st));
+  int rc = mg_generate(m, st, B, Lt, d_ids, d_box, d_px, attn_mask ? d_mask : nullptr, num_beams, max_length, d_out,
+                       nullptr, nullptr, steps_run);
+  if (rc != 0) return rc;
+  MG_CHECK_CUDA(cudaMemcpyAsync(out_ids, d_out, (size_t)B * max_length * 8, cudaMemcpyDeviceToHost, st));
+  MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (out_len) {
+    for (int b = 0; b < B; ++b) {
+      int len = max_length;
+      for (int t = 1; t < max_length; ++t)
+        if (out_ids[(size_t)b * max_length + t] == c.eos_token_id) {
+          len = t + 1;
+          break;
+        }
+      out_len[b] = len;
+    }
+  }
+  MG_API_END
+}
+
+int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (encode_ms) *encode_ms = m->last_encode_ms;
+  if (decode_ms) *decode_ms = m->last_decode_ms;
+  if (kernels_launched) *kernels_launched = m->last_launches;
+  MG_API_END
+}
+
+}  // extern "C"

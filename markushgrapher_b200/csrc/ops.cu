@@ -1,0 +1,428 @@
+// Non-GEMM kernels of the VTL (UDOP) encoder and shared helpers: RMSNorm, embedding fusion/compaction,
+// cell-2D embeddings, relative-position buckets, bias+mask+softmax. All fp32 math; GEMM inputs are emitted
+// directly as split-bf16 planes so no separate cast pass exists.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace mg {
+
+// =====================================================================================================
+// T5 / UDOP bucket function as an exact integer LUT (host).  Follows
+// transformers/models/udop/modeling_udop.py:466-512 (_relative_position_bucket), fp32 op order kept:
+//   large = max_exact + (log(n.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)).long()
+// lut[n] for n in [0, n_entries): bucket of |relative_position| = n WITHOUT the bidirectional sign offset.
+void rel_bucket_lut(int bidirectional, int num_buckets, int max_distance, int n_entries, int32_t* lut) {
+  int nb = bidirectional ? num_buckets / 2 : num_buckets;
+  const int max_exact = nb / 2;
+  const float denom = (float)log((double)max_distance / (double)max_exact);
+  for (int n = 0; n < n_entries; ++n) {
+    int v;
+    if (n < max_exact) {
+      v = n;
+    } else {
+      const float f = logf((float)n / (float)max_exact) / denom * (float)(nb - max_exact);
+      long l = (long)f;  // trunc toward zero like .to(torch.long)
+      l += max_exact;
+      if (l > nb - 1) l = nb - 1;
+      v = (int)l;
+    }
+    lut[n] = v;
+  }
+}
+
+// =====================================================================================================
+// RMSNorm (UdopLayerNorm, modeling_udop.py:333-355): y = w * (x * rsqrt(mean(x^2) + eps)) [* scale]
+// one warp per row; D % 128 == 0 (float4 per lane).
+template <int MAXV>  // float4 chunks per lane held in registers
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, int64_t rows, int D, float eps,
+                               float scale, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                               float* __restrict__ out_f32, int64_t rows_per_b, int64_t out_bs, int64_t out_off) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+  float4 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      v[i] = xr[lane + 32 * i];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rs = rsqrtf(ss / (float)D + eps);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const float4 ww = wr[lane + 32 * i];
+      float o[4] = {ww.x * (v[i].x * rs), ww.y * (v[i].y * rs), ww.z * (v[i].z * rs), ww.w * (v[i].w * rs)};
+      if (scale != 1.f) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] *= scale;
+      }
+      const int c = (lane + 32 * i) * 4;
+      if (out_hi) {
+        bf16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_bf16(o[k], h[k], l[k]);
+        uint2 ph, pl;
+        ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+        ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+        pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+        pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2*>(out_hi + r * D + c) = ph;
+        if (out_lo) *reinterpret_cast<uint2*>(out_lo + r * D + c) = pl;
+      }
+      if (out_f32) {
+        const int64_t o_row = (r / rows_per_b) * out_bs + (r % rows_per_b) * D + out_off;
+        *reinterpret_cast<float4*>(out_f32 + o_row + c) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+void launch_rmsnorm(cudaStream_t st, const float* x, const float* w, int64_t rows, int D, float eps, float scale,
+                    Planes out, float* out_f32, int64_t rows_per_b, int64_t out_bs, int64_t out_off) {
+  MG_REQUIRE(D % 128 == 0 && D <= 128 * 8, "rmsnorm: d_model must be a multiple of 128 and <= 1024");
+  if (rows == 0) return;
+  if (rows_per_b <= 0) {
+    rows_per_b = rows;
+    out_bs = 0;
+  }
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  rmsnorm_kernel<8><<<grid, wpb * 32, 0, st>>>(x, w, rows, D, eps, scale, out.hi, out.lo, out_f32, rows_per_b, out_bs,
+                                               out_off);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// im2col for a stride==kernel patch conv (UdopPatchEmbeddings modeling_udop.py:217-243; SwinPatchEmbeddings
+// modeling_swin.py:255-296): pixel (B,3,H,W) fp32 -> planes [B*gh*gw, ldk], column order (c, ky, kx) = the
+// flattening of the conv weight [out, 3, p, p]; columns >= 3*p*p are zero.
+__global__ void im2col_kernel(const float* __restrict__ px, int B, int H, int W, int p, int ldk, bf16* hi, bf16* lo) {
+  const int gh = H / p, gw = W / p;
+  const int K = 3 * p * p;
+  const int64_t total = (int64_t)B * gh * gw * ldk;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ldk);
+    const int64_t row = i / ldk;
+    float v = 0.f;
+    if (col < K) {
+      const int kx = col % p, ky = (col / p) % p, c = col / (p * p);
+      const int gx = (int)(row % gw), gy = (int)((row / gw) % gh), b = (int)(row / ((int64_t)gw * gh));
+      v = px[(((int64_t)b * 3 + c) * H + (gy * p + ky)) * W + gx * p + kx];
+    }
+    bf16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+void launch_im2col(cudaStream_t st, const float* px, int B, int H, int W, int p, int ldk, Planes out) {
+  const int64_t total = (int64_t)B * (H / p) * (W / p) * ldk;
+  if (!total) return;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  im2col_kernel<<<blocks, 256, 0, st>>>(px, B, H, W, p, ldk, out.hi, out.lo);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// combine_image_text_embeddings (modeling_udop.py:133-214), step 1: per image, which patches are absorbed
+// by a text token and the compacted (stable-order) list of surviving patches.
+//   ocr_point = clip(floor((x0+x2)/2*np),0,np-1) + np*clip(floor((y0+y2)/2*np),0,np-1)     (fp32, :149-156)
+//   every text token (masked or not, "target" or not) removes its patch                       (:169-181)
+// out: ocr_point[B,Lt] (int), vis_src[B,NP] = source patch of the k-th surviving patch or -1, n_vis[B]
+__global__ void combine_plan_kernel(const float* __restrict__ bbox, int Lt, int np, int* __restrict__ ocr_point,
+                                    int* __restrict__ vis_src, int* __restrict__ n_vis) {
+  extern __shared__ int sm[];  // removed[NP], then scan
+  const int b = blockIdx.x;
+  const int NP = np * np;
+  int* removed = sm;
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) removed[i] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < Lt; t += blockDim.x) {
+    const float* bb = bbox + ((int64_t)b * Lt + t) * 4;
+    const float fx = floorf((bb[0] + bb[2]) / 2.0f * (float)np);
+    const float fy = floorf((bb[1] + bb[3]) / 2.0f * (float)np);
+    long long ix = (long long)fx, iy = (long long)fy;
+    ix = ix < 0 ? 0 : (ix > np - 1 ? np - 1 : ix);
+    iy = iy < 0 ? 0 : (iy > np - 1 ? np - 1 : iy);
+    const int pt = (int)(ix + iy * np);
+    ocr_point[(int64_t)b * Lt + t] = pt;
+    removed[pt] = 1;  // benign race: all writers store 1
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // NP <= 1024: a serial stable compaction per image is negligible next to the encoder
+    int k = 0;
+    for (int i = 0; i < NP; ++i)
+      if (!removed[i]) vis_src[(int64_t)b * NP + (k++)] = i;
+    n_vis[b] = k;
+    for (; k < NP; ++k) vis_src[(int64_t)b * NP + k] = -1;
+  }
+}
+
+// step 2: build the encoder input sequence  x[B,Sp,D], bbox_ext[B,Sp,4] (float64 like the reference after
+// :158), mask[B,Sp]:   s <  Lt            : tok_emb[id] + (target_seg ? 0 : patch_emb[ocr_point])     (:159-164)
+//                      Lt <= s < Lt+NP    : k-th surviving patch embedding / zero padding              (:183-206)
+//                      s >= Lt+NP         : alignment padding (mask 0), not part of the reference sequence
+// then x += cell_2d_embedding(bbox_ext)  (UdopCellEmbeddings :784-807, UdopStack :1138-1139).
+__global__ void combine_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ bbox,
+                                     const int64_t* __restrict__ attn_mask, const float* __restrict__ tok_emb,
+                                     const float* __restrict__ patch_emb, const int* __restrict__ ocr_point,
+                                     const int* __restrict__ vis_src, const float* __restrict__ cell_x,
+                                     const float* __restrict__ cell_y, int Lt, int np, int Sp, int D, int max_2d,
+                                     int vocab, float* __restrict__ x, double* __restrict__ bbox_ext,
+                                     int* __restrict__ mask) {
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int NP = np * np;
+  double bb[4] = {0., 0., 0., 0.};
+  const float* src_tok = nullptr;
+  const float* src_patch = nullptr;
+  int m = 0;
+  if (s < Lt) {
+    const int64_t tix = (int64_t)b * Lt + s;
+    for (int k = 0; k < 4; ++k) bb[k] = (double)bbox[tix * 4 + k];
+    int64_t id = ids[tix];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    src_tok = tok_emb + id * D;
+    const double mean = (bb[0] + bb[1] + bb[2] + bb[3]) / 4.0;
+    const bool target = (mean == 0.0) || (mean == 1.0);
+    if (!target) src_patch = patch_emb + ((int64_t)b * NP + ocr_point[tix]) * D;
+    m = attn_mask ? (attn_mask[tix] != 0) : 1;
+  } else if (s < Lt + NP) {
+    const int src = vis_src[(int64_t)b * NP + (s - Lt)];
+    if (src >= 0) {
+      src_patch = patch_emb + ((int64_t)b * NP + src) * D;
+      const int gx = src % np, gy = src / np;
+      // get_visual_bbox (:94-117): fp32 k/np, promoted to float64 by the cat with the text boxes
+      bb[0] = (double)((float)gx / (float)np);
+      bb[1] = (double)((float)gy / (float)np);
+      bb[2] = (double)((float)(gx + 1) / (float)np);
+      bb[3] = (double)((float)(gy + 1) / (float)np);
+      m = 1;
+    }
+  }
+  int ci[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double c = bb[k] < 0.0 ? 0.0 : (bb[k] > 1.0 ? 1.0 : bb[k]);
+    ci[k] = (int)(long long)(c * (double)(max_2d - 1));
+  }
+  const int64_t row = (int64_t)b * Sp + s;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) bbox_ext[row * 4 + k] = bb[k];
+    mask[row] = m;
+  }
+  const float4* t4 = reinterpret_cast<const float4*>(src_tok);
+  const float4* p4 = reinterpret_cast<const float4*>(src_patch);
+  const float4* cx0 = reinterpret_cast<const float4*>(cell_x + (int64_t)ci[0] * D);
+  const float4* cy1 = reinterpret_cast<const float4*>(cell_y + (int64_t)ci[1] * D);
+  const float4* cx2 = reinterpret_cast<const float4*>(cell_x + (int64_t)ci[2] * D);
+  const float4* cy3 = reinterpret_cast<const float4*>(cell_y + (int64_t)ci[3] * D);
+  float4* o4 = reinterpret_cast<float4*>(x + row * D);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src_tok) {
+      e = t4[c];
+      if (src_patch) {
+        const float4 q = p4[c];
+        e.x += q.x; e.y += q.y; e.z += q.z; e.w += q.w;
+      }
+    } else if (src_patch) {
+      e = p4[c];
+    }
+    const float4 a = cx0[c], bq = cy1[c], cq = cx2[c], dq = cy3[c];
+    float4 cell;
+    cell.x = ((a.x + bq.x) + cq.x) + dq.x;
+    cell.y = ((a.y + bq.y) + cq.y) + dq.y;
+    cell.z = ((a.z + bq.z) + cq.z) + dq.z;
+    cell.w = ((a.w + bq.w) + cq.w) + dq.w;
+    e.x += cell.x; e.y += cell.y; e.z += cell.z; e.w += cell.w;
+    o4[c] = e;
+  }
+}
+
+void launch_combine(cudaStream_t st, const int64_t* ids, const float* bbox, const int64_t* attn_mask,
+                    const float* tok_emb, const float* patch_emb, const float* cell_x, const float* cell_y, int B,
+                    int Lt, int np, int Sp, int D, int max_2d, int vocab, int* ocr_point, int* vis_src, int* n_vis,
+                    float* x, double* bbox_ext, int* mask) {
+  const int NP = np * np;
+  MG_REQUIRE(D % 4 == 0, "d_model must be a multiple of 4");
+  combine_plan_kernel<<<B, 256, NP * sizeof(int), st>>>(bbox, Lt, np, ocr_point, vis_src, n_vis);
+  MG_CHECK_CUDA(cudaGetLastError());
+  dim3 grid(Sp, B);
+  combine_embed_kernel<<<grid, 128, 0, st>>>(ids, bbox, attn_mask, tok_emb, patch_emb, ocr_point, vis_src, cell_x,
+                                             cell_y, Lt, np, Sp, D, max_2d, vocab, x, bbox_ext, mask);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// Horizontal / vertical relative-position buckets (RelativePositionBiasHorizontal/Vertical :935-970,
+// get_relative_position :887-895, bucket :466-512), computed ONCE per forward and shared by all layers/heads:
+//   pos = (b0+b2)/2 (float64);  rel = ((pos_j - pos_i) * 100).long();  bucket = (rel>0)*16 + lut[min(|rel|,cap)]
+// out hv[B,Sp,Sp] as uchar2 (h, v).
+__global__ void relbucket_hv_kernel(const double* __restrict__ bbox_ext, int Sp, const int* __restrict__ lut_hv,
+                                    int lut_n, int half_buckets, double scaling, uchar2* __restrict__ hv) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const double* bi = bbox_ext + ((int64_t)b * Sp + i) * 4;
+  const double xi = (bi[0] + bi[2]) / 2.0, yi = (bi[1] + bi[3]) / 2.0;
+  uchar2* out = hv + ((int64_t)b * Sp + i) * Sp;
+  for (int j = threadIdx.x; j < Sp; j += blockDim.x) {
+    const double* bj = bbox_ext + ((int64_t)b * Sp + j) * 4;
+    const double xj = (bj[0] + bj[2]) / 2.0, yj = (bj[1] + bj[3]) / 2.0;
+    long long rx = (long long)((xj - xi) * scaling);
+    long long ry = (long long)((yj - yi) * scaling);
+    const int ox = rx > 0 ? half_buckets : 0, oy = ry > 0 ? half_buckets : 0;
+    rx = rx < 0 ? -rx : rx;
+    ry = ry < 0 ? -ry : ry;
+    if (rx > lut_n - 1) rx = lut_n - 1;
+    if (ry > lut_n - 1) ry = lut_n - 1;
+    out[j] = make_uchar2((unsigned char)(ox + lut_hv[rx]), (unsigned char)(oy + lut_hv[ry]));
+  }
+}
+
+void launch_relbucket_hv(cudaStream_t st, const double* bbox_ext, int B, int Sp, const int* lut_hv, int lut_n,
+                         int half_buckets, uchar2* hv) {
+  dim3 grid(Sp, B);
+  relbucket_hv_kernel<<<grid, 256, 0, st>>>(bbox_ext, Sp, lut_hv, lut_n, half_buckets, 100.0, hv);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// Encoder attention probabilities: P = softmax(scores + (bias_v + (bias_h + bias_1d)) + (1-mask)*finfo.min)
+// (UdopStack :1173-1190, RelativePositionBiasAggregated :973-989, UdopAttention :608-613).  The (B,H,S,S)
+// bias tensor of the reference is never materialised: buckets come from `hv` (shared over heads/layers) and
+// an integer LUT over j-i.  One warp per (b,h,i) row; output = split planes for the P*V GEMM.
+template <int MAXE>
+__global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar2* __restrict__ hv,
+                                   const int* __restrict__ mask, const float* __restrict__ tab1d,
+                                   const float* __restrict__ tabh, const float* __restrict__ tabv,
+                                   const int* __restrict__ lut1d, int lut1d_n, int half_buckets, int nbuckets, int H,
+                                   int Sp, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo) {
+  extern __shared__ float smf[];
+  float* t1 = smf;                    // [nbuckets*H]
+  float* th = t1 + nbuckets * H;
+  float* tv = th + nbuckets * H;
+  int* l1 = reinterpret_cast<int*>(tv + nbuckets * H);  // [lut1d_n]
+  for (int i = threadIdx.x; i < nbuckets * H; i += blockDim.x) {
+    t1[i] = tab1d[i];
+    th[i] = tabh[i];
+    tv[i] = tabv[i];
+  }
+  for (int i = threadIdx.x; i < lut1d_n; i += blockDim.x) l1[i] = lut1d[i];
+  __syncthreads();
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b*H + h)*Sp + i
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(row % Sp);
+  const int h = (int)((row / Sp) % H);
+  const int64_t b = row / ((int64_t)Sp * H);
+  const float* sr = scores + row * Sp;
+  const uchar2* hvr = hv + (b * Sp + i) * Sp;
+  const int* mr = mask + b * Sp;
+  float v[MAXE];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = lane + 32 * e;
+    if (j < Sp) {
+      const uchar2 bk = hvr[j];
+      int rel = j - i;
+      const int o1 = rel > 0 ? half_buckets : 0;
+      rel = rel < 0 ? -rel : rel;
+      if (rel > lut1d_n - 1) rel = lut1d_n - 1;
+      const int b1 = o1 + l1[rel];
+      float bias = tv[bk.y * H + h] + (th[bk.x * H + h] + t1[b1 * H + h]);
+      bias = bias + (mr[j] ? 0.f : -3.4028234663852886e38f);
+      v[e] = sr[j] + bias;
+      mx = fmaxf(mx, v[e]);
+    } else {
+      v[e] = -INFINITY;
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = lane + 32 * e;
+    if (j < Sp) {
+      v[e] = expf(v[e] - mx);
+      sum += v[e];
+    }
+  }
+  sum = warp_sum(sum);
+  bf16* ph = p_hi + row * Sp;
+  bf16* pl = p_lo ? p_lo + row * Sp : nullptr;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int j = lane + 32 * e;
+    if (j < Sp) {
+      bf16 hh, ll;
+      split_bf16(v[e] / sum, hh, ll);
+      ph[j] = hh;
+      if (pl) pl[j] = ll;
+    }
+  }
+}
+
+void launch_enc_softmax(cudaStream_t st, const float* scores, const uchar2* hv, const int* mask, const float* tab1d,
+                        const float* tabh, const float* tabv, const int* lut1d, int lut1d_n, int half_buckets,
+                        int nbuckets, int B, int H, int Sp, Planes P) {
+  MG_REQUIRE(Sp <= 32 * 52, "encoder sequence too long for the softmax kernel (max 1664)");
+  const int64_t rows = (int64_t)B * H * Sp;
+  const int wpb = 8;
+  MG_REQUIRE(rows % wpb == 0, "B*H*Sp must be a multiple of 8");  // Sp is a multiple of 8
+  const size_t smem = (size_t)3 * nbuckets * H * sizeof(float) + (size_t)lut1d_n * sizeof(int);
+  const unsigned grid = (unsigned)(rows / wpb);
+  if (Sp <= 32 * 20)
+    enc_softmax_kernel<20><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
+                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+  else if (Sp <= 32 * 36)
+    enc_softmax_kernel<36><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
+                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+  else
+    enc_softmax_kernel<52><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
+                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
+// small utilities
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_f32(cudaStream_t st, float* p, int64_t n, float v) {
+  if (!n) return;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  fill_f32_kernel<<<blocks, 256, 0, st>>>(p, n, v);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// memory mask: [1]*n_sw + vtl mask (UDOP extended mask), padded positions 0.  out [B, Mp] int32
+__global__ void build_mem_mask_kernel(const int* __restrict__ vtl_mask, int Sp, int S, int n_sw, int Mp, int* out) {
+  const int b = blockIdx.y;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < Mp; m += gridDim.x * blockDim.x) {
+    int v = 0;
+    if (m < n_sw)
+      v = 1;
+    else if (m - n_sw < S)
+      v = vtl_mask[(int64_t)b * Sp + (m - n_sw)];
+    out[(int64_t)b * Mp + m] = v;
+  }
+}
+void launch_build_mem_mask(cudaStream_t st, const int* vtl_mask, int B, int Sp, int S, int n_sw, int Mp, int* out) {
+  dim3 grid((Mp + 255) / 256, B);
+  build_mem_mask_kernel<<<grid, 256, 0, st>>>(vtl_mask, Sp, S, n_sw, Mp, out);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace mg

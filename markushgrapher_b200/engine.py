@@ -1,0 +1,188 @@
+"""Thin ctypes layer over the C ABI (include/mg_b200.h): PyTorch tensors in, PyTorch tensors out.
+
+No arithmetic happens here and there is no fallback: every call lands in libmg_b200.so or raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+MG_MAX_SWIN_STAGES = 4
+
+
+class mg_config(ctypes.Structure):
+    _fields_ = [
+        ("vocab_size", ctypes.c_int32), ("d_model", ctypes.c_int32), ("d_kv", ctypes.c_int32),
+        ("d_ff", ctypes.c_int32), ("num_layers", ctypes.c_int32), ("num_decoder_layers", ctypes.c_int32),
+        ("num_heads", ctypes.c_int32),
+        ("rel_buckets", ctypes.c_int32), ("rel_max_distance", ctypes.c_int32), ("max_2d", ctypes.c_int32),
+        ("image_size", ctypes.c_int32), ("patch_size", ctypes.c_int32),
+        ("ln_eps", ctypes.c_float),
+        ("swin_image", ctypes.c_int32), ("swin_patch", ctypes.c_int32), ("swin_embed", ctypes.c_int32),
+        ("swin_num_stages", ctypes.c_int32),
+        ("swin_depths", ctypes.c_int32 * MG_MAX_SWIN_STAGES), ("swin_heads", ctypes.c_int32 * MG_MAX_SWIN_STAGES),
+        ("swin_window", ctypes.c_int32),
+        ("swin_ln_eps", ctypes.c_float),
+        ("proj_hidden", ctypes.c_int32),
+        ("precision", ctypes.c_int32),
+        ("logit_scale", ctypes.c_float),
+        ("decoder_start_token_id", ctypes.c_int32), ("eos_token_id", ctypes.c_int32), ("pad_token_id", ctypes.c_int32),
+        ("enc_chunk", ctypes.c_int32),
+    ]
+
+
+def make_c_config(cfg, precision: int = 0, enc_chunk: int = 0) -> mg_config:
+    """cfg: any object with the MGConfig attribute names (oracle.mg_oracle.MGConfig or MarkushgrapherConfig)."""
+    c = mg_config()
+    for k in ("vocab_size", "d_model", "d_kv", "d_ff", "num_layers", "num_decoder_layers", "num_heads", "max_2d",
+              "image_size", "patch_size", "swin_image", "swin_patch", "swin_embed", "swin_window", "proj_hidden"):
+        setattr(c, k, int(getattr(cfg, k)))
+    c.rel_buckets = int(cfg.rel_buckets)
+    c.rel_max_distance = int(cfg.rel_max_distance)
+    c.ln_eps = float(cfg.ln_eps)
+    c.swin_ln_eps = float(cfg.swin_ln_eps)
+    depths, heads = list(cfg.swin_depths), list(cfg.swin_heads)
+    assert len(depths) == len(heads) <= MG_MAX_SWIN_STAGES
+    c.swin_num_stages = len(depths)
+    for i, (dp, hd) in enumerate(zip(depths, heads)):
+        c.swin_depths[i] = int(dp)
+        c.swin_heads[i] = int(hd)
+    c.precision = int(precision)
+    c.logit_scale = float(getattr(cfg, "logit_scale", cfg.d_model ** -0.5))
+    c.decoder_start_token_id = int(getattr(cfg, "decoder_start_token_id", 0))
+    c.eos_token_id = int(getattr(cfg, "eos_token_id", 1))
+    c.pad_token_id = int(getattr(cfg, "pad_token_id", 0))
+    c.enc_chunk = int(enc_chunk)
+    return c
+
+
+class MGEngine:
+    """One model instance on the current CUDA device."""
+
+    def __init__(self, cfg, state: Dict[str, torch.Tensor], precision: int = 0, enc_chunk: int = 0,
+                 device: Optional[torch.device] = None):
+        L = _lib.lib()
+        if not torch.cuda.is_available() or not L.mg_device_available():
+            raise _lib.MgError("markushgrapher_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device(device or "cuda")
+        self._c = make_c_config(cfg, precision, enc_chunk)
+        self._h = ctypes.c_void_p()
+        L.mg_create.argtypes = [ctypes.POINTER(mg_config), ctypes.POINTER(ctypes.c_void_p)]
+        _lib.check(L.mg_create(ctypes.byref(self._c), ctypes.byref(self._h)), "mg_create")
+        L.mg_load_weight.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+        keep = []
+        with torch.cuda.device(self.device):
+            for name, t in state.items():
+                t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                shp = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
+                rc = L.mg_load_weight(self._h, name.encode(), ctypes.c_void_p(t.data_ptr()), 0, shp, t.dim())
+                if rc < 0:
+                    _lib.check(rc, f"mg_load_weight({name})")
+            torch.cuda.synchronize()
+            L.mg_finalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            _lib.check(L.mg_finalize(self._h, _lib.cur_stream()), "mg_finalize")
+        del keep
+        L.mg_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
+        L.mg_generate.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 +
+                                  [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4)
+        L.mg_generate_host.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] +
+                                       [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3)
+        L.mg_last_stats.argtypes = [ctypes.c_void_p] * 4
+        L.mg_destroy.argtypes = [ctypes.c_void_p]
+        L.mg_destroy.restype = None
+        self.n_patches = (cfg.image_size // cfg.patch_size) ** 2
+        g = cfg.swin_image // cfg.swin_patch // 2 ** (len(list(cfg.swin_depths)) - 1)
+        self.swin_tokens = g * g
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.lib().mg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _prep(self, input_ids, bbox, pixel_values, attention_mask, dev):
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        box = bbox.to(device=dev, dtype=torch.float32).contiguous()
+        px = pixel_values.to(device=dev, dtype=torch.float32).contiguous()
+        am = None if attention_mask is None else attention_mask.to(device=dev, dtype=torch.int64).contiguous()
+        B, Lt = ids.shape
+        assert box.shape == (B, Lt, 4), box.shape
+        assert px.shape == (B, 3, self.cfg.image_size, self.cfg.image_size), px.shape
+        return ids, box, px, am, B, Lt
+
+    def encode(self, input_ids, bbox, pixel_values, attention_mask=None):
+        """-> (memory (B, M, d) f32, mask (B, M) i32) on the device"""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
+        M = self.swin_tokens + Lt + self.n_patches
+        out = torch.empty((B, M, self.cfg.d_model), device=self.device, dtype=torch.float32)
+        mask = torch.empty((B, M), device=self.device, dtype=torch.int32)
+        m_out = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mg_encode(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px),
+                                      _lib.ptr(am), _lib.ptr(out), _lib.ptr(mask), ctypes.addressof(m_out))
+        _lib.check(rc, "mg_encode")
+        assert m_out.value == M
+        return out, mask
+
+    def generate(self, input_ids, bbox, pixel_values, attention_mask=None, num_beams=1, max_length=512,
+                 return_logits=False, trim=True):
+        """Device-resident inputs -> LongTensor (B, T) of token ids (column 0 = decoder start id)."""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
+        out = torch.empty((B, max_length), device=self.device, dtype=torch.int64)
+        lens = torch.empty((B,), device=self.device, dtype=torch.int32)
+        logits = None
+        if return_logits:
+            logits = torch.zeros((B, max_length - 1, self.cfg.vocab_size), device=self.device, dtype=torch.float32)
+        steps = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mg_generate(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px),
+                                        _lib.ptr(am), int(num_beams), int(max_length), _lib.ptr(out), _lib.ptr(lens),
+                                        _lib.ptr(logits), ctypes.addressof(steps))
+        _lib.check(rc, "mg_generate")
+        self.last_steps = steps.value
+        if trim:
+            out = out[:, : _stop_column(out, lens, max_length)]
+        if return_logits:
+            return out, logits[:, : out.shape[1] - 1]
+        return out
+
+    def generate_host(self, input_ids, bbox, pixel_values, attention_mask=None, num_beams=1, max_length=512,
+                      trim=True):
+        """HOST tensors in (pinned recommended), HOST LongTensor out; H2D/D2H happen inside the C call."""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, "cpu")
+        out = torch.empty((B, max_length), dtype=torch.int64).pin_memory()
+        lens = torch.empty((B,), dtype=torch.int32)
+        steps = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mg_generate_host(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box),
+                                             _lib.ptr(px), _lib.ptr(am), int(num_beams), int(max_length),
+                                             _lib.ptr(out), _lib.ptr(lens), ctypes.addressof(steps))
+        _lib.check(rc, "mg_generate_host")
+        self.last_steps = steps.value
+        if trim:
+            out = out[:, : _stop_column(out, lens, max_length)]
+        return out
+
+    def last_stats(self):
+        e, d, k = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int64(0)
+        _lib.check(_lib.lib().mg_last_stats(self._h, ctypes.addressof(e), ctypes.addressof(d), ctypes.addressof(k)),
+                   "mg_last_stats")
+        return {"encode_ms": e.value, "decode_ms": d.value, "kernels": k.value}
+
+
+def _stop_column(out: torch.Tensor, lens: torch.Tensor, max_length: int) -> int:
+    """GenerationMixin stops once every row has emitted EOS: the returned width is the longest row."""
+    return int(min(max_length, int(lens.max().item())))

@@ -76,10 +76,10 @@ class MGConfig:
 
     @staticmethod
     def small() -> "MGConfig":
-        """mid-size: every kernel path exercised (4 Swin stages, shifted windows, 4 heads), seconds on CPU"""
+        """mid-size: every kernel path exercised (3 Swin stages, shifted windows, 4 heads), seconds on CPU"""
         return MGConfig(vocab_size=2051, d_model=256, d_ff=512, num_layers=3, num_decoder_layers=3, num_heads=4,
-                        image_size=128, swin_image=192, swin_embed=32, swin_depths=(2, 2, 2, 2),
-                        swin_heads=(1, 2, 4, 8), proj_hidden=256)
+                        image_size=128, swin_image=192, swin_embed=32, swin_depths=(2, 2, 2),
+                        swin_heads=(1, 2, 4), proj_hidden=256)
 
     @staticmethod
     def tiny() -> "MGConfig":
