@@ -87,6 +87,13 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);
 
+/* Measurement hook for bench.py: re-launches the decode cross-attention kernel (the dominant, HBM-bound kernel of
+ * the path) over the cross-KV buffers of the preceding mg_generate call, every decoder layer in turn (each
+ * layer's K/V is larger than L2, so every launch is cache-cold), `reps` times between CUDA events on `stream`.
+ * Outputs are HOST pointers: average ms per launch, algorithmic bytes per launch, launches timed. */
+int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_launch, int64_t* bytes_per_launch,
+                          int32_t* n_launches);
+
 /* ---- unit-level entry points used by the parity tests (device pointers, fp32) ---- */
 
 /* c[M,N] = act(a[M,K] * b[N,K]^T + bias[N]) + residual[M,N]; row-major.

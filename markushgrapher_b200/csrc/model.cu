@@ -144,6 +144,10 @@ struct mg_model {
   int* pinned_flag = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t own_stream = nullptr;
+  // buffers of the last generate call (valid until the next encode/generate), for mg_profile_cross_attn
+  std::vector<float*> prof_ckt, prof_cv;
+  float* prof_q = nullptr;
+  Planes prof_ctx;
 
   ~mg_model() {
     for (void* p : owned) cudaFree(p);
@@ -777,6 +781,10 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     launches += 3;
   };
 
+  prof_ckt = ckt;
+  prof_cv = cv;
+  prof_q = q;
+  prof_ctx = ctx;
   const int total_steps = max_length - 1;
   int done_steps = 0;
   // step 0 runs eagerly (lazy one-time initialisation happens outside graph capture) ...
@@ -980,6 +988,40 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
       out_len[b] = len;
     }
   }
+  MG_API_END
+}
+
+int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_launch, int64_t* bytes_per_launch,
+                          int32_t* n_launches) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && m->prof_q && !m->prof_ckt.empty(), "mg_profile_cross_attn needs a preceding mg_generate call");
+  MG_REQUIRE(reps > 0, "reps must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr || st == cudaStreamLegacy) {
+    MG_CHECK_CUDA(cudaDeviceSynchronize());
+    if (!m->own_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    st = m->own_stream;
+  }
+  const mg_config& c = m->cfg;
+  const int B = m->cur_B, d = c.d_model, H = c.num_heads, Mp = m->cur_Mp, NL = (int)m->prof_ckt.size();
+  auto pass = [&]() {
+    for (int l = 0; l < NL; ++l)
+      launch_dec_cross_attn(st, m->prof_q, B, H, d, m->prof_ckt[l], Mp, (int64_t)d * Mp, m->prof_cv[l], d,
+                            (int64_t)Mp * d, Mp, m->mem_mask, Mp, m->prof_ctx);
+  };
+  pass();  // warm-up
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[0], st));
+  for (int r = 0; r < reps; ++r) pass();
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[1], st));
+  MG_CHECK_CUDA(cudaEventSynchronize(m->ev[1]));
+  float ms = 0.f;
+  MG_CHECK_CUDA(cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]));
+  if (ms_per_launch) *ms_per_launch = ms / (float)(reps * NL);
+  // algorithmic bytes of one launch: K and V of the true memory length M (fp32), the mask, q in, ctx planes out
+  if (bytes_per_launch)
+    *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->cur_M * d * 4 + (int64_t)m->cur_M * 4 + (int64_t)d * 4 +
+                                      (int64_t)d * (m->split2 ? 4 : 2));
+  if (n_launches) *n_launches = reps * NL;
   MG_API_END
 }
 

@@ -310,14 +310,17 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
                                    const int* __restrict__ lut1d, int lut1d_n, int half_buckets, int nbuckets, int H,
                                    int Sp, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo) {
   extern __shared__ float smf[];
-  float* t1 = smf;                    // [nbuckets*H]
+  // tables transposed to [head][bucket]: a warp works on ONE head, so its lanes index by bucket only and
+  // distinct buckets fall in distinct banks (the [bucket][head] layout of the weights is a 16-way conflict)
+  float* t1 = smf;                    // [H*nbuckets]
   float* th = t1 + nbuckets * H;
   float* tv = th + nbuckets * H;
   int* l1 = reinterpret_cast<int*>(tv + nbuckets * H);  // [lut1d_n]
   for (int i = threadIdx.x; i < nbuckets * H; i += blockDim.x) {
-    t1[i] = tab1d[i];
-    th[i] = tabh[i];
-    tv[i] = tabv[i];
+    const int bk = i / H, hh = i % H;
+    t1[hh * nbuckets + bk] = tab1d[i];
+    th[hh * nbuckets + bk] = tabh[i];
+    tv[hh * nbuckets + bk] = tabv[i];
   }
   for (int i = threadIdx.x; i < lut1d_n; i += blockDim.x) l1[i] = lut1d[i];
   __syncthreads();
@@ -326,6 +329,9 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
   const int i = (int)(row % Sp);
   const int h = (int)((row / Sp) % H);
   const int64_t b = row / ((int64_t)Sp * H);
+  const float* t1h = t1 + h * nbuckets;
+  const float* thh = th + h * nbuckets;
+  const float* tvh = tv + h * nbuckets;
   const float* sr = scores + row * Sp;
   const uchar2* hvr = hv + (b * Sp + i) * Sp;
   const int* mr = mask + b * Sp;
@@ -341,7 +347,7 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
       rel = rel < 0 ? -rel : rel;
       if (rel > lut1d_n - 1) rel = lut1d_n - 1;
       const int b1 = o1 + l1[rel];
-      float bias = tv[bk.y * H + h] + (th[bk.x * H + h] + t1[b1 * H + h]);
+      float bias = tvh[bk.y] + (thh[bk.x] + t1h[b1]);
       bias = bias + (mr[j] ? 0.f : -3.4028234663852886e38f);
       v[e] = sr[j] + bias;
       mx = fmaxf(mx, v[e]);
@@ -360,6 +366,7 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
     }
   }
   sum = warp_sum(sum);
+  const float inv_sum = 1.f / sum;
   bf16* ph = p_hi + row * Sp;
   bf16* pl = p_lo ? p_lo + row * Sp : nullptr;
 #pragma unroll
@@ -367,7 +374,7 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
     const int j = lane + 32 * e;
     if (j < Sp) {
       bf16 hh, ll;
-      split_bf16(v[e] / sum, hh, ll);
+      split_bf16(v[e] * inv_sum, hh, ll);
       ph[j] = hh;
       if (pl) pl[j] = ll;
     }

@@ -176,6 +176,15 @@ class MGEngine:
             out = out[:, : _stop_column(out, lens, max_length)]
         return out
 
+    def profile_cross_attn(self, reps: int = 3):
+        L = _lib.lib()
+        L.mg_profile_cross_attn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+        ms, by, n = ctypes.c_float(0), ctypes.c_int64(0), ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(L.mg_profile_cross_attn(self._h, _lib.cur_stream(), reps, ctypes.addressof(ms),
+                                               ctypes.addressof(by), ctypes.addressof(n)), "mg_profile_cross_attn")
+        return {"ms_per_launch": ms.value, "bytes_per_launch": by.value, "launches": n.value}
+
     def last_stats(self):
         e, d, k = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int64(0)
         _lib.check(_lib.lib().mg_last_stats(self._h, ctypes.addressof(e), ctypes.addressof(d), ctypes.addressof(k)),

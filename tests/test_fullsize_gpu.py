@@ -1,0 +1,73 @@
+"""GPU: parity and size-independent properties at the FULL MarkushGrapher-2 dimensions (831 M parameters)."""
+import pytest
+import torch
+
+from markushgrapher_b200.configuration import MarkushgrapherConfig, random_state
+from markushgrapher_b200.engine import MGEngine
+from oracle import mg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full_pair():
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    cfg = O.MGConfig.full()
+    oracle = O.build(cfg, seed=0)
+    eng = MGEngine(cfg, oracle.export_state())
+    yield cfg, oracle, eng
+    eng.close()
+
+
+def test_full_size_encoder_and_greedy_parity(full_pair):
+    cfg, oracle, eng = full_pair
+    inp = O.make_inputs(cfg, 2, 64, seed=1234)
+    mem_ref, mask_ref = oracle.encode(**inp)
+    mem, mask = eng.encode(**inp)
+    assert torch.equal(mask.cpu().long(), mask_ref.long())
+    err = ((mem.cpu().double() - mem_ref.double()).norm() / mem_ref.double().norm()).item()
+    print(f"full-size encoder rel err {err:.2e}")
+    assert err < 1e-3
+    max_len = 12
+    ids_ref, lg_ref = oracle.generate_greedy(None, None, None, memory=mem_ref, mask=mask_ref, max_length=max_len,
+                                             return_logits=True)
+    ids, lg = eng.generate(**inp, max_length=max_len, return_logits=True)
+    lerr = ((lg.cpu().double() - lg_ref.double()).norm() / lg_ref.double().norm()).item()
+    top2 = lg_ref.topk(2, dim=-1).values
+    print(f"full-size logits rel err {lerr:.2e}, min top-2 margin {(top2[..., 0] - top2[..., 1]).min().item():.2e}")
+    assert lerr < 1e-3
+    assert torch.equal(ids.cpu(), ids_ref)
+
+
+def test_full_size_batch_independence_and_repeatability(full_pair):
+    """images are independent units: decoding an image alone or inside a batch of 5 gives the same ids, and a
+    repeated call reproduces them (size-independent property; ragged text lengths, batch not a multiple of 4)"""
+    cfg, oracle, eng = full_pair
+    inp = O.make_inputs(cfg, 5, 40, seed=77, ragged=True)
+    ids_a, lg_a = eng.generate(**inp, max_length=10, return_logits=True)
+    ids_b, lg_b = eng.generate(**inp, max_length=10, return_logits=True)
+    assert torch.equal(ids_a, ids_b)
+    one = {k: v[3:4] for k, v in inp.items()}
+    ids_1, lg_1 = eng.generate(**one, max_length=10, return_logits=True)
+    assert torch.allclose(lg_1[0], lg_a[3], atol=2e-3, rtol=0)
+    assert torch.equal(ids_1[0], ids_a[3])
+
+
+def test_random_state_runs_config2_shape():
+    """the bench workload shape (batch 32, text 64) end to end with product-side random weights; EOS/pad
+    bookkeeping invariants on the output (no oracle involved)"""
+    cfg = MarkushgrapherConfig()
+    dev = torch.device("cuda", 0)
+    eng = MGEngine(cfg, random_state(cfg, 0, dev), device=dev)
+    import bench
+
+    inp = {k: v.to(dev) for k, v in bench.synth_inputs(512, 32, 64, 1234, cfg.vocab_size).items()}
+    ids = eng.generate(**inp, max_length=24, trim=False)
+    assert ids.shape == (32, 24) and (ids[:, 0] == 0).all()
+    assert (ids >= 0).all() and (ids < cfg.vocab_size).all()
+    assert ids[:, 1:].unique().numel() > 24  # diverse decode
+    for row in ids.cpu():
+        pos = (row == 1).nonzero()
+        if len(pos):
+            assert (row[pos[0, 0] + 1:] == 0).all()
+    eng.close()
