@@ -19,15 +19,14 @@ namespace mg {
 // SELF : n_keys = step+1; the new k/v row (from the fused QKV GEMM output qkv[b][3*D]) is appended to the
 //        caches by this kernel and used from shared memory; bias = dec_bias[lut[step - j]][h].
 // CROSS: n_keys = Mp; additive mask (1-mask)*finfo.min, no positional bias (:588-593).
-// Scores are NOT scaled by 1/sqrt(d) (T5).  Output ctx[b][h*64+d] is written as split planes for the O GEMM.
+// Scores are NOT scaled by 1/sqrt(d) (T5).  Output ctx[b][h*64+d] fp32 feeds the O projection.
 template <bool SELF>
 __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__ qsrc, int q_ld, float* __restrict__ kt,
                                                        int64_t kt_ld, int64_t kt_bs, float* __restrict__ v,
                                                        int64_t v_ld, int64_t v_bs, const int* __restrict__ step_ptr,
                                                        int n_keys_cross, const int* __restrict__ mask, int mask_ld,
                                                        const float* __restrict__ dec_bias, const int* __restrict__ lut,
-                                                       int H, int D, bf16* __restrict__ ctx_hi,
-                                                       bf16* __restrict__ ctx_lo) {
+                                                       int H, int D, float* __restrict__ ctx) {
   constexpr int HD = 64;
   extern __shared__ __align__(16) float sm[];
   float* sq = sm;             // [64]
@@ -143,11 +142,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
     float o = 0.f;
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) o += sred[rr * HD + tid];
-    o *= inv;
-    bf16 hh, ll;
-    split_bf16(o, hh, ll);
-    ctx_hi[(int64_t)b * D + h * HD + tid] = hh;
-    if (ctx_lo) ctx_lo[(int64_t)b * D + h * HD + tid] = ll;
+    ctx[(int64_t)b * D + h * HD + tid] = o * inv;
   }
 }
 
@@ -155,25 +150,24 @@ static size_t dec_attn_smem(int max_keys) { return (size_t)(64 + 64 + 16 * 64 + 
 
 void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D, float* kt, int64_t kt_ld,
                           int64_t kt_bs, float* v, int64_t v_ld, int64_t v_bs, const int* step_ptr, int max_keys,
-                          const float* dec_bias, const int* lut, Planes ctx) {
+                          const float* dec_bias, const int* lut, float* ctx) {
   MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
   dim3 grid(H, B);
   dec_attn_kernel<true><<<grid, 256, dec_attn_smem(max_keys), st>>>(qkv, 3 * D, kt, kt_ld, kt_bs, v, v_ld, v_bs,
                                                                      step_ptr, 0, nullptr, 0, dec_bias, lut, H, D,
-                                                                     ctx.hi, ctx.lo);
+                                                                     ctx);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 
 void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
                            int64_t kt_bs, const float* v, int64_t v_ld, int64_t v_bs, int n_keys, const int* mask,
-                           int mask_ld, Planes ctx) {
+                           int mask_ld, float* ctx) {
   MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
   MG_REQUIRE(n_keys % 4 == 0 && kt_ld % 4 == 0, "cross-attention memory length must be a multiple of 4");
   dim3 grid(H, B);
   dec_attn_kernel<false><<<grid, 256, dec_attn_smem(n_keys), st>>>(q, D, const_cast<float*>(kt), kt_ld, kt_bs,
                                                                    const_cast<float*>(v), v_ld, v_bs, nullptr, n_keys,
-                                                                   mask, mask_ld, nullptr, nullptr, H, D, ctx.hi,
-                                                                   ctx.lo);
+                                                                   mask, mask_ld, nullptr, nullptr, H, D, ctx);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 

@@ -366,6 +366,285 @@ void launch_gemm(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, in
     launch_bn<32>(st, p, grid);
 }
 
+// ================================================================================================
+// Skinny (decode-step) linear on the tensor cores:  out[b][n] (+)= post_b * sum_k pro(x)[b][k] * W[n][k]
+// for R = 32*NG activation rows.  W rows sit on the UMMA M axis (128 features per CTA, TMA-staged split planes),
+// the activation tile is BUILT IN-KERNEL by the four worker warps: they read the fp32 residual stream / hidden
+// buffer, apply the fused prologue (RMSNorm weight, ReLU), split to bf16 hi/lo and store straight into the
+// 128B-swizzled K-major layout the UMMA descriptor expects -- so no separate norm / activation / cast kernels
+// exist in the decode step.  The RMSNorm row statistic is applied in the epilogue (rs[b] * acc is linear in the
+// split-K partial sums), and is computed by the workers while TMA and MMA are in flight.  Split-K over
+// blockIdx.y with fp32 atomics keeps every SM streaming a slice of W; accumulating straight into the residual
+// stream gives the residual add; an optional zero duty clears a later GEMM's accumulation buffer.
+// (UdopLayerNorm :333-355, UdopDenseActDense :359-381, UdopAttention q/k/v/o :465-468, lm head :1585-1590)
+struct alignas(64) SkinnyParams {
+  CUtensorMap tw_hi, tw_lo;
+  const float* x;
+  int ldx;
+  float* out;
+  int ld_out;
+  int B, N, K;
+  int kb_per_cta, num_kb, stages;
+  int nplanes;
+  int pro;  // 0 none, 1 rms (x*lnw staged, rs*scale in the epilogue), 2 relu
+  const float* lnw;
+  float eps, scale;
+  float* zero_ptr;
+  long long zero_n;
+  int store;
+};
+
+template <int NG>
+__global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant__ SkinnyParams p) {
+  constexpr int R = 32 * NG;             // activation rows = UMMA N
+  constexpr int X_BYTES = R * BK * 2;    // one plane of the activation tile
+  constexpr int STAGE = 2 * A_BYTES + 2 * X_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * STAGE);   // W tile landed (TMA tx)
+  uint64_t* xrdy_bar = full_bar + S;                                    // activation tile staged (128 arrivals)
+  uint64_t* empty_bar = xrdy_bar + S;                                   // stage consumed by the MMAs
+  uint64_t* tmem_full_bar = empty_bar + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_rs = reinterpret_cast<float*>(tmem_slot + 2);                // [R] row scale for the epilogue
+  float* s_part = s_rs + R;                                             // [R][4] partial sums of squares
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int kb0 = blockIdx.y * p.kb_per_cta;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_cta);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tw_hi);
+    if (p.nplanes == 2) prefetch_tmap(&p.tw_lo);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&xrdy_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, R);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = (p.nplanes == 2) ? 2 * A_BYTES : A_BYTES;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE;
+        mbar_expect_tx(&full_bar[s], tx);
+        tma_load_4d(st, &p.tw_hi, &full_bar[s], kb * BK, m0, 0, 0);
+        if (p.nplanes == 2) tma_load_4d(st + A_BYTES, &p.tw_lo, &full_bar[s], kb * BK, m0, 0, 0);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, R);
+      int s = 0;
+      uint32_t ph = 0, acc = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&xrdy_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE);
+        const uint64_t da_hi = make_sw128_kmajor_desc(sa), da_lo = make_sw128_kmajor_desc(sa + A_BYTES);
+        const uint64_t db_hi = make_sw128_kmajor_desc(sa + 2 * A_BYTES);
+        const uint64_t db_lo = make_sw128_kmajor_desc(sa + 2 * A_BYTES + X_BYTES);
+        if (p.nplanes == 2) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) { umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, acc); acc = 1; }
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) { umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, acc); acc = 1; }
+        umma_commit(&empty_bar[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---------------------------------------------------------------- workers (warps 2..5, 128 threads)
+    const int t = threadIdx.x - 64;
+    {  // activation tiles for every k-block of this CTA, G k-blocks per round trip to L2
+      constexpr int NI = (R * 16) / 128;  // float4 items per thread per k-block
+      constexpr int G = 4 / NG;           // k-blocks whose loads are issued together
+      const int c4 = t & 15;              // 16 float4 per 64-wide row; identical for all items of a thread
+      const int nkb = kb1 - kb0;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int g0 = 0; g0 < nkb; g0 += G) {
+        float4 v[G][NI];
+        float4 gw[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          const int kb = kb0 + min(g0 + u, nkb - 1);
+          if (p.pro == 1) gw[u] = *reinterpret_cast<const float4*>(p.lnw + kb * BK + c4 * 4);
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const int r = min((t + i * 128) >> 4, p.B - 1);  // rows >= B are zeroed below
+            v[u][i] = *reinterpret_cast<const float4*>(p.x + (int64_t)r * p.ldx + kb * BK + c4 * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          if (g0 + u < nkb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* xs_hi = smem + s * STAGE + 2 * A_BYTES;
+            uint8_t* xs_lo = xs_hi + X_BYTES;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const int r = (t + i * 128) >> 4;
+              float4 w = v[u][i];
+              if (r >= p.B) w = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.pro == 1) {
+                w.x *= gw[u].x; w.y *= gw[u].y; w.z *= gw[u].z; w.w *= gw[u].w;
+              } else if (p.pro == 2) {
+                w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+              }
+              bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+              split_bf16(w.x, h0, l0); split_bf16(w.y, h1, l1); split_bf16(w.z, h2, l2); split_bf16(w.w, h3, l3);
+              // 128B swizzle: 16-byte chunk index XOR (row % 8); this float4 covers half a chunk (8 bytes)
+              const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
+              uint2 ph2, pl2;
+              ph2.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              ph2.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+              pl2.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              pl2.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+              *reinterpret_cast<uint2*>(xs_hi + off) = ph2;
+              if (p.nplanes == 2) *reinterpret_cast<uint2*>(xs_lo + off) = pl2;
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&xrdy_bar[s]);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+    // zero duty (other GEMM's accumulation buffer), off the critical path
+    if (p.zero_ptr) {
+      const int64_t n4 = p.zero_n >> 2;
+      const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * 128;
+      float4* z4 = reinterpret_cast<float4*>(p.zero_ptr);
+      for (int64_t i = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + t; i < n4; i += nthreads)
+        z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // RMSNorm row statistic over the FULL row (while TMA / MMA are in flight)
+    const int wq = warp - 2;  // 0..3
+    if (p.pro == 1) {
+      // K <= 1024 here (d_model): each thread owns at most two float4 of a row; loads are unconditional
+      // (rows / columns out of range are clamped and weighted by 0) so 16 of them are in flight per batch
+      const int n4row = p.K >> 2;
+      const int ca = min(t, n4row - 1), cb = min(t + 128, n4row - 1);
+      const float wa = t < n4row ? 1.f : 0.f, wb = (t + 128) < n4row ? 1.f : 0.f;
+      for (int r0 = 0; r0 < R; r0 += 8) {
+        float4 qa[8], qb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)min(r0 + j, p.B - 1) * p.ldx);
+          qa[j] = xr[ca];
+          qb[j] = xr[cb];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float ss = wa * (qa[j].x * qa[j].x + qa[j].y * qa[j].y + qa[j].z * qa[j].z + qa[j].w * qa[j].w) +
+                     wb * (qb[j].x * qb[j].x + qb[j].y * qb[j].y + qb[j].z * qb[j].z + qb[j].w * qb[j].w);
+          ss = warp_sum(ss);
+          if (lane == 0) s_part[(r0 + j) * 4 + wq] = ss;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t < R) {
+        const float ss = (s_part[t * 4] + s_part[t * 4 + 1]) + (s_part[t * 4 + 2] + s_part[t * 4 + 3]);
+        s_rs[t] = rsqrtf(ss / (float)p.K + p.eps) * p.scale;
+      }
+    } else {
+      if (t < R) s_rs[t] = p.scale;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int n = m0 + q * 32 + lane;  // output feature of this thread (TMEM lane)
+#pragma unroll 1
+    for (int c0 = 0; c0 < R; c0 += 32) {
+      uint32_t rr[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, rr);
+      tmem_ld_wait();
+      if (n < p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int b = c0 + j;
+          if (b < p.B) {
+            const float v = __uint_as_float(rr[j]) * s_rs[b];
+            float* o = p.out + (int64_t)b * p.ld_out + n;  // lanes -> consecutive features: coalesced
+            if (p.store) *o = v; else atomicAdd(o, v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, R);
+}
+
+template <int NG>
+static void launch_skinny_ng(cudaStream_t st, const SkinnyParams& p, dim3 grid) {
+  constexpr int STAGE = 2 * A_BYTES + 2 * (32 * NG * BK * 2);
+  const int smem = p.stages * STAGE + 1024 + 256 + 32 * NG * 5 * 4 + 64;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    MG_CHECK_CUDA(cudaFuncSetAttribute(skinny_tc_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_smem = 200 * 1024;
+  }
+  skinny_tc_kernel<NG><<<grid, 192, smem, st>>>(p);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
+                      int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
+                      bool store) {
+  MG_REQUIRE(K % BK == 0 && ldx % 4 == 0, "skinny linear: K must be a multiple of 64");
+  MG_REQUIRE(pro != 1 || K <= 1024, "skinny linear: fused RMSNorm needs K <= 1024");
+  MG_REQUIRE(B >= 1 && B <= 128, "skinny linear: 1 <= B <= 128 per launch");
+  MG_REQUIRE(zero_n % 4 == 0, "zero duty must be a multiple of 4 floats");
+  SkinnyParams p;
+  GemmOperand A;
+  A.hi = W.hi; A.lo = W.lo; A.rows = N; A.ld = ldw;
+  p.nplanes = W.lo ? 2 : 1;
+  encode_operand(&p.tw_hi, W.hi, A, K, 1, 1, BM);
+  if (W.lo) encode_operand(&p.tw_lo, W.lo, A, K, 1, 1, BM); else p.tw_lo = p.tw_hi;
+  p.x = x; p.ldx = ldx; p.out = out; p.ld_out = ld_out; p.B = B; p.N = N; p.K = K;
+  p.num_kb = K / BK;
+  const int tiles = (N + BM - 1) / BM;
+  int ksplit = 1;
+  if (!store) ksplit = std::min(p.num_kb, std::max(1, 148 / tiles));
+  p.kb_per_cta = (p.num_kb + ksplit - 1) / ksplit;
+  ksplit = (p.num_kb + p.kb_per_cta - 1) / p.kb_per_cta;
+  p.stages = std::min(4, p.kb_per_cta);
+  p.pro = pro; p.lnw = lnw; p.eps = eps; p.scale = scale;
+  p.zero_ptr = zero_ptr; p.zero_n = zero_n; p.store = store ? 1 : 0;
+  dim3 grid(tiles, ksplit);
+  if (B <= 32) launch_skinny_ng<1>(st, p, grid);
+  else if (B <= 64) launch_skinny_ng<2>(st, p, grid);
+  else launch_skinny_ng<4>(st, p, grid);
+}
+
 // ------------------------------------------------------------------------------------------------ fp32 -> planes
 __global__ void split_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in, bf16* hi,
                              bf16* lo, int64_t ld_out) {

@@ -33,10 +33,10 @@ void launch_window_attn(cudaStream_t st, const float* qkv, const float* table, i
 // ---- decode.cu
 void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D, float* kt, int64_t kt_ld,
                           int64_t kt_bs, float* v, int64_t v_ld, int64_t v_bs, const int* step_ptr, int max_keys,
-                          const float* dec_bias, const int* lut, Planes ctx);
+                          const float* dec_bias, const int* lut, float* ctx);
 void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
                            int64_t kt_bs, const float* v, int64_t v_ld, int64_t v_bs, int n_keys, const int* mask,
-                           int mask_ld, Planes ctx);
+                           int mask_ld, float* ctx);
 void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
 void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
@@ -46,5 +46,10 @@ void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int
                         int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x);
 
 void launch_out_len(cudaStream_t st, const int64_t* ids, int B, int ld, int ncols, int eos, int* len);
+
+// gemm_tc.cu: tensor-core skinny linear with fused prologue (pro: 0 none, 1 RMSNorm, 2 ReLU), split-K atomics
+void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
+                      int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
+                      bool store);
 
 }  // namespace mg

@@ -88,7 +88,8 @@ struct EncLayer {
 };
 struct DecLayer {
   float *ln1, *ln2, *ln3;
-  LinearW qkv, o, cq, ck, cv, co, wi, wo;
+  LinearW qkv, o, cq, co, wi, wo;
+  LinearW ck, cv;
 };
 struct SwBlock {
   float *ln1w, *ln1b, *ln2w, *ln2b, *table;
@@ -147,7 +148,7 @@ struct mg_model {
   // buffers of the last generate call (valid until the next encode/generate), for mg_profile_cross_attn
   std::vector<float*> prof_ckt, prof_cv;
   float* prof_q = nullptr;
-  Planes prof_ctx;
+  float* prof_ctx = nullptr;
 
   ~mg_model() {
     for (void* p : owned) cudaFree(p);
@@ -308,6 +309,7 @@ void mg_model::finalize(cudaStream_t st) {
   dec_bias = copy_f32(st, "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", (int64_t)c.rel_buckets * H);
   dec_final_ln = copy_f32(st, "decoder.final_layer_norm.weight", d);
   lm_head = make_linear(st, {"lm_head.weight"}, {}, d);
+  MG_REQUIRE(d % 64 == 0 && c.d_ff % 64 == 0, "d_model and d_ff must be multiples of 64");
 
   // ---- Swin
   const std::string sp = "encoder.molscribe_encoder.";
@@ -715,70 +717,54 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     sv[l] = a.get<float>((int64_t)B * Tp * d);
   }
   float* x = a.get<float>((int64_t)B * d);
-  Planes xn = planes(a, (int64_t)B * d);
   float* qkv = a.get<float>((int64_t)B * 3 * d);
   float* q = a.get<float>((int64_t)B * d);
-  Planes ctx = planes(a, (int64_t)B * d);
+  float* ctx = a.get<float>((int64_t)B * d);
   float* hbuf = a.get<float>((int64_t)B * c.d_ff);
-  Planes hpl = planes(a, (int64_t)B * c.d_ff);
   float* logits = a.get<float>((int64_t)B * Vld);
   int* finished = a.get<int>(B);
   int* ctr = a.get<int>(8);  // [0]=step [1]=n_unfinished [2]=ticket
   int64_t* ids_dev = out_ids;
   launch_decode_init(st, shared, d, c.decoder_start_token_id, B, ids_dev, max_length, finished, ctr, ctr + 1, ctr + 2, x);
   ++launches;
+  // split-K accumulation buffers start at zero; afterwards each is re-zeroed by a later kernel of the chain
+  MG_CHECK_CUDA(cudaMemsetAsync(qkv, 0, sizeof(float) * (size_t)B * 3 * d, st));
+  MG_CHECK_CUDA(cudaMemsetAsync(q, 0, sizeof(float) * (size_t)B * d, st));
+  MG_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * (size_t)B * c.d_ff, st));
 
-  const int bn = B <= 32 ? 32 : (B <= 64 ? 64 : 128);
-  const int nbt = (B + bn - 1) / bn;
-  // skinny GEMM: out[b][n] += sum_k W[n][k] act[b][k], W rows on the MMA M axis, split-K over CTAs
-  auto skinny = [&](const LinearW& W, Planes act, float* out, int64_t out_ld, bool zero_first) {
-    if (zero_first) MG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * out_ld, st));
-    GemmOperand A, Bop;
-    A.hi = W.w.hi; A.lo = W.w.lo; A.rows = W.N; A.ld = W.ldk;
-    Bop.hi = act.hi; Bop.lo = act.lo; Bop.rows = B; Bop.ld = W.K;
-    GemmEpilogue ep;
-    ep.out_f32 = out;
-    ep.ld_r = 1;
-    ep.ld_c = out_ld;
-    ep.atomic = 1;
-    const int tiles = ((W.N + 127) / 128) * nbt;
-    int ks = std::max(1, 148 / tiles);
-    launch_gemm(st, A, Bop, W.N, B, W.K, 1, 1, ks, ep, bn);
-    ++launches;
+  // out[b0:b0+128] (+)= pro(x) W^T in slices of at most 128 rows
+  auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
+                 float scale, float* zp, int64_t zn, bool store) {
+    for (int b0 = 0; b0 < B; b0 += 128) {
+      const int bc = std::min(128, B - b0);
+      launch_skinny_tc(st, pro, xin + (int64_t)b0 * ldx, ldx, W.w, W.ldk, out + (int64_t)b0 * ld_out, ld_out, bc, W.N,
+                       W.K, lnw, c.ln_eps, scale, b0 == 0 ? zp : nullptr, zn, store);
+      ++launches;
+    }
   };
   auto one_step = [&]() {
     for (int l = 0; l < NL; ++l) {
       DecLayer& L = dec[l];
-      launch_rmsnorm(st, x, L.ln1, B, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
-      skinny(L.qkv, xn, qkv, 3 * d, true);
+      // self-attention block: RMSNorm fused into the QKV projection; zero duty: FF hidden buffer
+      lin(1, x, d, L.qkv, qkv, 3 * d, L.ln1, 1.f, hbuf, (int64_t)B * c.d_ff, false);
       launch_dec_self_attn(st, qkv, B, H, d, skt[l], Tp, (int64_t)d * Tp, sv[l], d, (int64_t)Tp * d, ctr, Tp, dec_bias,
                            lut_dec, ctx);
-      skinny(L.o, ctx, x, d, false);  // x += o(ctx)
-      launch_rmsnorm(st, x, L.ln2, B, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
-      skinny(L.cq, xn, q, d, true);
+      lin(0, ctx, d, L.o, x, d, nullptr, 1.f, nullptr, 0, false);  // x += o(ctx)
+      // cross-attention block; zero duty: the QKV buffer just consumed by self-attention
+      lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv, (int64_t)B * 3 * d, false);
       launch_dec_cross_attn(st, q, B, H, d, ckt[l], Mp, (int64_t)d * Mp, cv[l], d, (int64_t)Mp * d, Mp, mem_mask, Mp,
                             ctx);
-      skinny(L.co, ctx, x, d, false);
-      launch_rmsnorm(st, x, L.ln3, B, d, c.ln_eps, 1.f, xn, nullptr, 0, 0, 0);
-      skinny(L.wi, xn, hbuf, c.d_ff, true);
-      launch_relu_split(st, hbuf, (int64_t)B * c.d_ff, hpl);
-      skinny(L.wo, hpl, x, d, false);
-      launches += 6;
+      lin(0, ctx, d, L.co, x, d, nullptr, 1.f, nullptr, 0, false);
+      // feed-forward: RMSNorm fused into wi, ReLU fused into wo's operand load; zero duty: cross-attention q
+      lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q, (int64_t)B * d, false);
+      lin(2, hbuf, c.d_ff, L.wo, x, d, nullptr, 1.f, nullptr, 0, false);
+      launches += 2;
     }
-    launch_rmsnorm(st, x, dec_final_ln, B, d, c.ln_eps, c.logit_scale, xn, nullptr, 0, 0, 0);
-    {
-      GemmOperand A, Bop;
-      A.hi = lm_head.w.hi; A.lo = lm_head.w.lo; A.rows = V; A.ld = lm_head.ldk;
-      Bop.hi = xn.hi; Bop.lo = xn.lo; Bop.rows = B; Bop.ld = d;
-      GemmEpilogue ep;
-      ep.out_f32 = logits;
-      ep.ld_r = 1;
-      ep.ld_c = Vld;
-      launch_gemm(st, A, Bop, V, B, d, 1, 1, 1, ep, bn);
-    }
+    // final RMSNorm * d_model^-0.5 fused into the LM head (modeling_udop.py:1585-1590), direct store
+    lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true);
     launch_greedy_select(st, logits, B, V, Vld, shared, d, c.eos_token_id, c.pad_token_id, ids_dev, max_length,
                          finished, ctr, ctr + 1, ctr + 2, x, step_logits, (int64_t)(max_length - 1) * V, V);
-    launches += 3;
+    launches += 1;
   };
 
   prof_ckt = ckt;

@@ -303,8 +303,8 @@ void launch_relbucket_hv(cudaStream_t st, const double* bbox_ext, int B, int Sp,
 // (UdopStack :1173-1190, RelativePositionBiasAggregated :973-989, UdopAttention :608-613).  The (B,H,S,S)
 // bias tensor of the reference is never materialised: buckets come from `hv` (shared over heads/layers) and
 // an integer LUT over j-i.  One warp per (b,h,i) row; output = split planes for the P*V GEMM.
-template <int MAXE>
-__global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar2* __restrict__ hv,
+template <int MAXQ>  // quads (4 consecutive keys) per lane
+__global__ void __launch_bounds__(256) enc_softmax_kernel(const float* __restrict__ scores, const uchar2* __restrict__ hv,
                                    const int* __restrict__ mask, const float* __restrict__ tab1d,
                                    const float* __restrict__ tabh, const float* __restrict__ tabv,
                                    const int* __restrict__ lut1d, int lut1d_n, int half_buckets, int nbuckets, int H,
@@ -332,51 +332,81 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
   const float* t1h = t1 + h * nbuckets;
   const float* thh = th + h * nbuckets;
   const float* tvh = tv + h * nbuckets;
-  const float* sr = scores + row * Sp;
-  const uchar2* hvr = hv + (b * Sp + i) * Sp;
-  const int* mr = mask + b * Sp;
-  float v[MAXE];
+  const float4* sr = reinterpret_cast<const float4*>(scores + row * Sp);
+  const uint2* hvr = reinterpret_cast<const uint2*>(hv + (b * Sp + i) * Sp);   // 4 x uchar2
+  const int4* mr = reinterpret_cast<const int4*>(mask + b * Sp);
+  const int nq = Sp >> 2;  // Sp is a multiple of 8
+  // phase 1: issue every global load of the row before touching the data (memory-level parallelism)
+  float4 v[MAXQ];
+  uint2 hq[MAXQ];
+  int4 mq[MAXQ];
+#pragma unroll
+  for (int e = 0; e < MAXQ; ++e) {
+    const int q = lane + 32 * e;
+    if (q < nq) {
+      v[e] = __ldcs(sr + q);   // streamed once
+      hq[e] = __ldg(hvr + q);
+      mq[e] = __ldg(mr + q);
+    }
+  }
   float mx = -INFINITY;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = lane + 32 * e;
-    if (j < Sp) {
-      const uchar2 bk = hvr[j];
-      int rel = j - i;
-      const int o1 = rel > 0 ? half_buckets : 0;
-      rel = rel < 0 ? -rel : rel;
-      if (rel > lut1d_n - 1) rel = lut1d_n - 1;
-      const int b1 = o1 + l1[rel];
-      float bias = tvh[bk.y] + (thh[bk.x] + t1h[b1]);
-      bias = bias + (mr[j] ? 0.f : -3.4028234663852886e38f);
-      v[e] = sr[j] + bias;
-      mx = fmaxf(mx, v[e]);
-    } else {
-      v[e] = -INFINITY;
+  for (int e = 0; e < MAXQ; ++e) {
+    const int q = lane + 32 * e;
+    if (q < nq) {
+      float* vv = reinterpret_cast<float*>(&v[e]);
+      const uint32_t hw[2] = {hq[e].x, hq[e].y};
+      const int mm[4] = {mq[e].x, mq[e].y, mq[e].z, mq[e].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = q * 4 + k;
+        const uint32_t pr = (hw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+        const int bh = pr & 0xff, bv = pr >> 8;
+        int rel = j - i;
+        const int o1 = rel > 0 ? half_buckets : 0;
+        rel = rel < 0 ? -rel : rel;
+        if (rel > lut1d_n - 1) rel = lut1d_n - 1;
+        const int b1 = o1 + l1[rel];
+        float bias = tvh[bv] + (thh[bh] + t1h[b1]);
+        bias = bias + (mm[k] ? 0.f : -3.4028234663852886e38f);
+        vv[k] = vv[k] + bias;
+        mx = fmaxf(mx, vv[k]);
+      }
     }
   }
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = lane + 32 * e;
-    if (j < Sp) {
-      v[e] = expf(v[e] - mx);
-      sum += v[e];
+  for (int e = 0; e < MAXQ; ++e) {
+    const int q = lane + 32 * e;
+    if (q < nq) {
+      float* vv = reinterpret_cast<float*>(&v[e]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vv[k] = expf(vv[k] - mx);
+        sum += vv[k];
+      }
     }
   }
   sum = warp_sum(sum);
   const float inv_sum = 1.f / sum;
-  bf16* ph = p_hi + row * Sp;
-  bf16* pl = p_lo ? p_lo + row * Sp : nullptr;
+  uint2* ph = reinterpret_cast<uint2*>(p_hi + row * Sp);
+  uint2* pl = p_lo ? reinterpret_cast<uint2*>(p_lo + row * Sp) : nullptr;
 #pragma unroll
-  for (int e = 0; e < MAXE; ++e) {
-    const int j = lane + 32 * e;
-    if (j < Sp) {
-      bf16 hh, ll;
-      split_bf16(v[e] * inv_sum, hh, ll);
-      ph[j] = hh;
-      if (pl) pl[j] = ll;
+  for (int e = 0; e < MAXQ; ++e) {
+    const int q = lane + 32 * e;
+    if (q < nq) {
+      const float* vv = reinterpret_cast<const float*>(&v[e]);
+      bf16 hh[4], ll[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_bf16(vv[k] * inv_sum, hh[k], ll[k]);
+      uint2 oh, ol;
+      oh.x = (uint32_t)__bfloat16_as_ushort(hh[0]) | ((uint32_t)__bfloat16_as_ushort(hh[1]) << 16);
+      oh.y = (uint32_t)__bfloat16_as_ushort(hh[2]) | ((uint32_t)__bfloat16_as_ushort(hh[3]) << 16);
+      ol.x = (uint32_t)__bfloat16_as_ushort(ll[0]) | ((uint32_t)__bfloat16_as_ushort(ll[1]) << 16);
+      ol.y = (uint32_t)__bfloat16_as_ushort(ll[2]) | ((uint32_t)__bfloat16_as_ushort(ll[3]) << 16);
+      ph[q] = oh;
+      if (pl) pl[q] = ol;
     }
   }
 }
@@ -384,20 +414,21 @@ __global__ void enc_softmax_kernel(const float* __restrict__ scores, const uchar
 void launch_enc_softmax(cudaStream_t st, const float* scores, const uchar2* hv, const int* mask, const float* tab1d,
                         const float* tabh, const float* tabv, const int* lut1d, int lut1d_n, int half_buckets,
                         int nbuckets, int B, int H, int Sp, Planes P) {
-  MG_REQUIRE(Sp <= 32 * 52, "encoder sequence too long for the softmax kernel (max 1664)");
+  MG_REQUIRE(Sp % 8 == 0 && Sp <= 128 * 13, "encoder sequence must be a multiple of 8 and <= 1664");
+  MG_REQUIRE(nbuckets <= 256, "too many relative-position buckets");
   const int64_t rows = (int64_t)B * H * Sp;
   const int wpb = 8;
-  MG_REQUIRE(rows % wpb == 0, "B*H*Sp must be a multiple of 8");  // Sp is a multiple of 8
+  MG_REQUIRE(rows % wpb == 0, "B*H*Sp must be a multiple of 8");
   const size_t smem = (size_t)3 * nbuckets * H * sizeof(float) + (size_t)lut1d_n * sizeof(int);
   const unsigned grid = (unsigned)(rows / wpb);
-  if (Sp <= 32 * 20)
-    enc_softmax_kernel<20><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
-                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo);
-  else if (Sp <= 32 * 36)
-    enc_softmax_kernel<36><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
-                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+  if (Sp <= 128 * 5)
+    enc_softmax_kernel<5><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
+                                                        half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+  else if (Sp <= 128 * 9)
+    enc_softmax_kernel<9><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
+                                                        half_buckets, nbuckets, H, Sp, P.hi, P.lo);
   else
-    enc_softmax_kernel<52><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
+    enc_softmax_kernel<13><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
                                                          half_buckets, nbuckets, H, Sp, P.hi, P.lo);
   MG_CHECK_CUDA(cudaGetLastError());
 }
