@@ -172,6 +172,178 @@ void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D,
 }
 
 // =====================================================================================================
+// Cross-attention for one (head, image) as a bulk-copy streaming pipeline (the dominant, HBM-bound kernel of
+// the whole path: it reads the image's cross K and V of every layer once per generated token).
+//   K^T : kt[b][h][64][Mp]   one contiguous 64*Mp block   -> chunks of RK whole d-rows
+//   V   : v [b][h][Mp][64]   one contiguous Mp*64 block   -> chunks of 64 keys
+// A producer thread streams both blocks through a ring of shared-memory stages with cp.async.bulk, completing
+// on "full" mbarriers; 8 consumer warps drain a stage and release it through an "empty" mbarrier, so the
+// deep queue of bulk copies (not warp occupancy) keeps HBM busy and the V stream starts while the softmax of
+// the scores is still being reduced.  Scores: thread = key (conflict-free smem reads), fp32 accumulate over d;
+// additive mask (1-mask)*finfo.min (modeling_udop.py:1202-1205), no positional bias, no 1/sqrt(d) scale.
+constexpr int CA_STAGE_BYTES = 16384;
+constexpr int CA_NST = 3;
+constexpr int CA_MAXK = 8;  // keys per consumer thread: Mp <= 2048
+
+__global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __restrict__ q, const float* __restrict__ kt,
+                                                                const float* __restrict__ v,
+                                                                const int* __restrict__ mask, int Mp, int H, int D,
+                                                                float* __restrict__ ctx) {
+  constexpr int HD = 64;
+  extern __shared__ __align__(128) uint8_t smc[];
+  float* ring = reinterpret_cast<float*>(smc);                                   // [NST][4096 floats]
+  float* sc = ring + CA_NST * (CA_STAGE_BYTES / 4);                              // [Mp]
+  float* sq = sc + Mp;                                                           // [64]
+  float* sred = sq + HD;                                                         // [16*64]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sred + 16 * HD);              // [NST]
+  uint64_t* empty_bar = full_bar + CA_NST;                                       // [NST]
+  float* s_b = reinterpret_cast<float*>(empty_bar + CA_NST);                     // [2 + 8]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* ktb = kt + ((int64_t)b * H + h) * HD * Mp;
+  const float* vb = v + ((int64_t)b * H + h) * (int64_t)Mp * HD;
+  const int RK = min(HD, CA_STAGE_BYTES / (Mp * 4));  // d-rows per K chunk
+  const int nkc = (HD + RK - 1) / RK;
+  const int nvc = (Mp + 63) / 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < CA_NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    fence_mbar_init();
+  }
+  if (tid < HD) sq[tid] = q[(int64_t)b * D + h * HD + tid];
+  __syncthreads();
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < nkc + nvc; ++c) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const float* src;
+        uint32_t bytes;
+        if (c < nkc) {
+          const int r0 = c * RK, rows = min(RK, HD - r0);
+          src = ktb + (int64_t)r0 * Mp;
+          bytes = (uint32_t)rows * Mp * 4;
+        } else {
+          const int m0 = (c - nkc) * 64, rows = min(64, Mp - m0);
+          src = vb + (int64_t)m0 * HD;
+          bytes = (uint32_t)rows * HD * 4;
+        }
+        mbar_expect_tx(&full_bar[s], bytes);
+        bulk_load_1d(ring + s * (CA_STAGE_BYTES / 4), src, bytes, &full_bar[s]);
+        if (++s == CA_NST) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumers (256 threads)
+  int s = 0;
+  uint32_t ph = 0;
+  float acc[CA_MAXK];
+#pragma unroll
+  for (int i = 0; i < CA_MAXK; ++i) acc[i] = 0.f;
+  for (int c = 0; c < nkc; ++c) {
+    mbar_wait(&full_bar[s], ph);
+    const float* buf = ring + s * (CA_STAGE_BYTES / 4);
+    const int r0 = c * RK, rows = min(RK, HD - r0);
+    for (int rr = 0; rr < rows; ++rr) {
+      const float qd = sq[r0 + rr];
+      const float* row = buf + rr * Mp;
+#pragma unroll
+      for (int i = 0; i < CA_MAXK; ++i) {
+        const int m = tid + 256 * i;
+        if (m < Mp) acc[i] += qd * row[m];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (++s == CA_NST) { s = 0; ph ^= 1; }
+  }
+  // mask, max
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < CA_MAXK; ++i) {
+    const int m = tid + 256 * i;
+    if (m < Mp) {
+      acc[i] += (mask[(int64_t)b * Mp + m] ? 0.f : -3.4028234663852886e38f);
+      mx = fmaxf(mx, acc[i]);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_b[2 + warp] = mx;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  mx = s_b[2];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_b[2 + w]);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CA_MAXK; ++i) {
+    const int m = tid + 256 * i;
+    if (m < Mp) {
+      const float p = expf(acc[i] - mx);
+      sc[m] = p;
+      sum += p;
+    }
+  }
+  sum = warp_sum(sum);
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read s_b[2..9]
+  if (lane == 0) s_b[2 + warp] = sum;
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // sc[] and partial sums visible
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += s_b[2 + w];
+  const float inv = 1.f / sum;
+  // P.V over the V chunks: thread (r = tid/16, c = tid%16) -> float4 column c, keys j == r (mod 16)
+  const int r = tid >> 4, cc = tid & 15;
+  float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < nvc; ++c) {
+    mbar_wait(&full_bar[s], ph);
+    const float4* buf4 = reinterpret_cast<const float4*>(ring + s * (CA_STAGE_BYTES / 4));
+    const int m0 = c * 64, rows = min(64, Mp - m0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = r + 16 * j;
+      if (jj < rows) {
+        const float4 vv = buf4[jj * 16 + cc];
+        const float p = sc[m0 + jj];
+        a4.x += p * vv.x; a4.y += p * vv.y; a4.z += p * vv.z; a4.w += p * vv.w;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (++s == CA_NST) { s = 0; ph ^= 1; }
+  }
+  reinterpret_cast<float4*>(sred)[r * 16 + cc] = a4;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) o += sred[rr * HD + tid];
+    ctx[(int64_t)b * D + h * HD + tid] = o * inv;
+  }
+}
+
+void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, const float* v,
+                              int Mp, const int* mask, float* ctx) {
+  MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
+  MG_REQUIRE(Mp % 4 == 0 && Mp <= 256 * CA_MAXK, "cross-attention memory length must be a multiple of 4, <= 2048");
+  const size_t smem = (size_t)CA_NST * CA_STAGE_BYTES + (size_t)(Mp + 64 + 16 * 64) * 4 + 2 * CA_NST * 8 + 64;
+  static bool attr = false;
+  if (!attr) {
+    MG_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  dim3 grid(H, B);
+  cross_attn_stream_kernel<<<grid, 288, smem, st>>>(q, kt, v, mask, Mp, H, D, ctx);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// =====================================================================================================
 // h = relu(x) -> split planes (decode FF: the wi GEMM is split-K/atomic so the activation cannot live in its epilogue)
 __global__ void relu_split_kernel(const float* __restrict__ x, int64_t n, bf16* hi, bf16* lo) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

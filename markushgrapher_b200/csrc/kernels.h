@@ -37,6 +37,9 @@ void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D
 void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
                            int64_t kt_bs, const float* v, int64_t v_ld, int64_t v_bs, int n_keys, const int* mask,
                            int mask_ld, float* ctx);
+// streaming cross-attention: kt [B][H][64][Mp], v [B][H][Mp][64] (both contiguous per (b,h))
+void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, const float* v,
+                              int Mp, const int* mask, float* ctx);
 void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
 void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,

@@ -704,10 +704,18 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       launch_gemm(st, A, Bop, d, Mp, d, 1, B, 1, ep, 128);
       ++launches;
     }
-    {
+    {  // V, head-major: cv[b][h][m][64] so that every (image, head) block is one contiguous stream
+      GemmOperand A, Bop;
+      A.hi = mem_pl.hi; A.lo = mem_pl.lo; A.rows = Mp; A.ld = d; A.use_b2 = true; A.bs2 = (int64_t)Mp * d;
+      Bop.hi = dec[l].cv.w.hi; Bop.lo = dec[l].cv.w.lo; Bop.rows = 64; Bop.ld = dec[l].cv.ldk;
+      Bop.use_b1 = true; Bop.bs1 = (int64_t)64 * dec[l].cv.ldk;
       GemmEpilogue ep;
       ep.out_f32 = cv[l];
-      linear(st, dec[l].cv, mem_pl, d, (int64_t)B * Mp, ep);
+      ep.ld_r = 64;
+      ep.bs1 = (int64_t)Mp * 64;
+      ep.bs2 = (int64_t)Mp * d;
+      launch_gemm(st, A, Bop, Mp, 64, d, H, B, 1, ep, 64);
+      ++launches;
     }
   }
   // ---- decode state
@@ -752,8 +760,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       lin(0, ctx, d, L.o, x, d, nullptr, 1.f, nullptr, 0, false);  // x += o(ctx)
       // cross-attention block; zero duty: the QKV buffer just consumed by self-attention
       lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv, (int64_t)B * 3 * d, false);
-      launch_dec_cross_attn(st, q, B, H, d, ckt[l], Mp, (int64_t)d * Mp, cv[l], d, (int64_t)Mp * d, Mp, mem_mask, Mp,
-                            ctx);
+      launch_cross_attn_stream(st, q, B, H, d, ckt[l], cv[l], Mp, mem_mask, ctx);
       lin(0, ctx, d, L.co, x, d, nullptr, 1.f, nullptr, 0, false);
       // feed-forward: RMSNorm fused into wi, ReLU fused into wo's operand load; zero duty: cross-attention q
       lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q, (int64_t)B * d, false);
@@ -992,8 +999,7 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
   const int B = m->cur_B, d = c.d_model, H = c.num_heads, Mp = m->cur_Mp, NL = (int)m->prof_ckt.size();
   auto pass = [&]() {
     for (int l = 0; l < NL; ++l)
-      launch_dec_cross_attn(st, m->prof_q, B, H, d, m->prof_ckt[l], Mp, (int64_t)d * Mp, m->prof_cv[l], d,
-                            (int64_t)Mp * d, Mp, m->mem_mask, Mp, m->prof_ctx);
+      launch_cross_attn_stream(st, m->prof_q, B, H, d, m->prof_ckt[l], m->prof_cv[l], Mp, m->mem_mask, m->prof_ctx);
   };
   pass();  // warm-up
   MG_CHECK_CUDA(cudaEventRecord(m->ev[0], st));
