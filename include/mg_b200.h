@@ -84,6 +84,13 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
                      const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length,
                      int64_t* out_ids, int32_t* out_len, int32_t* steps_run);
 
+/* Teacher-forced logits, the reference's `model(**batch).logits` with decoder_input_ids = shift_right(labels):
+ * decoder_input_ids (B, T) i64 -> logits (B, T, vocab) f32. Runs T cached decode steps with the next input forced
+ * (same kernels as mg_generate). Synchronises `stream` before returning. */
+int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                      const float* pixel_values, const int64_t* attn_mask, const int64_t* decoder_input_ids, int T,
+                      float* logits);
+
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);
 

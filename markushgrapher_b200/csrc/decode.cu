@@ -181,7 +181,7 @@ void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D,
 // deep queue of bulk copies (not warp occupancy) keeps HBM busy and the V stream starts while the softmax of
 // the scores is still being reduced.  Scores: thread = key (conflict-free smem reads), fp32 accumulate over d;
 // additive mask (1-mask)*finfo.min (modeling_udop.py:1202-1205), no positional bias, no 1/sqrt(d) scale.
-constexpr int CA_STAGE_BYTES = 16384;
+constexpr int CA_STAGE_BYTES = 15360;  // 3 stages + scores: 4 CTAs (one wave of 592 slots) per SM at Mp ~ 1232
 constexpr int CA_NST = 3;
 constexpr int CA_MAXK = 8;  // keys per consumer thread: Mp <= 2048
 
@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __r
   const float* vb = v + ((int64_t)b * H + h) * (int64_t)Mp * HD;
   const int RK = min(HD, CA_STAGE_BYTES / (Mp * 4));  // d-rows per K chunk
   const int nkc = (HD + RK - 1) / RK;
-  const int nvc = (Mp + 63) / 64;
+  constexpr int VR = CA_STAGE_BYTES / (HD * 4);  // keys per V chunk
+  const int nvc = (Mp + VR - 1) / VR;
 
   if (tid == 0) {
     for (int s = 0; s < CA_NST; ++s) {
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __r
           src = ktb + (int64_t)r0 * Mp;
           bytes = (uint32_t)rows * Mp * 4;
         } else {
-          const int m0 = (c - nkc) * 64, rows = min(64, Mp - m0);
+          const int m0 = (c - nkc) * VR, rows = min(VR, Mp - m0);
           src = vb + (int64_t)m0 * HD;
           bytes = (uint32_t)rows * HD * 4;
         }
@@ -304,9 +305,9 @@ __global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __r
   for (int c = 0; c < nvc; ++c) {
     mbar_wait(&full_bar[s], ph);
     const float4* buf4 = reinterpret_cast<const float4*>(ring + s * (CA_STAGE_BYTES / 4));
-    const int m0 = c * 64, rows = min(64, Mp - m0);
+    const int m0 = c * VR, rows = min(VR, Mp - m0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < (VR + 15) / 16; ++j) {
       const int jj = r + 16 * j;
       if (jj < rows) {
         const float4 vv = buf4[jj * 16 + cc];
@@ -370,7 +371,8 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
                                                             int* __restrict__ finished, int* __restrict__ step_ptr,
                                                             int* __restrict__ n_unfinished, int* __restrict__ ticket,
                                                             float* __restrict__ x_next, float* __restrict__ logits_dump,
-                                                            int64_t dump_bs, int64_t dump_ss) {
+                                                            int64_t dump_bs, int64_t dump_ss,
+                                                            const int64_t* __restrict__ forced, int forced_ld) {
   const int b = blockIdx.x;
   const float* lg = logits + (int64_t)b * ld;
   const int step = *step_ptr;
@@ -408,9 +410,12 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
         bi = si[w];
       }
     const int fin = finished[b];
-    const int tok = fin ? pad : bi;
+    int tok = fin ? pad : bi;
     out_ids[(int64_t)b * out_ld + step + 1] = tok;
-    if (!fin && tok == eos) {
+    if (forced) {
+      // teacher forcing (model(**batch).logits): the next decoder input is given, nothing ever "finishes"
+      tok = (int)forced[(int64_t)b * forced_ld + min(step + 1, forced_ld - 1)];
+    } else if (!fin && tok == eos) {
       finished[b] = 1;
       atomicSub(n_unfinished, 1);
     }
@@ -435,16 +440,19 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
 void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
-                          int64_t dump_ss) {
+                          int64_t dump_ss, const int64_t* forced, int forced_ld) {
   greedy_select_kernel<<<B, 256, 0, st>>>(logits, V, ld, emb, D, eos, pad, out_ids, out_ld, finished, step_ptr,
-                                          n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss);
+                                          n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss, forced,
+                                          forced_ld);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 
 // decode state reset: ids[:,0] = start token, x = emb[start], finished = 0, step = 0
 __global__ void decode_init_kernel(const float* __restrict__ emb, int D, int start, int B, int64_t* out_ids, int out_ld,
-                                   int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x) {
+                                   int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
+                                   const int64_t* __restrict__ forced, int forced_ld) {
   const int b = blockIdx.x;
+  if (forced) start = (int)forced[(int64_t)b * forced_ld];
   for (int i = threadIdx.x; i < out_ld; i += blockDim.x) out_ids[(int64_t)b * out_ld + i] = (i == 0) ? start : 0;
   for (int c = threadIdx.x; c < D; c += blockDim.x) x[(int64_t)b * D + c] = emb[(int64_t)start * D + c];
   if (threadIdx.x == 0) {
@@ -457,8 +465,10 @@ __global__ void decode_init_kernel(const float* __restrict__ emb, int D, int sta
   }
 }
 void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int B, int64_t* out_ids, int out_ld,
-                        int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x) {
-  decode_init_kernel<<<B, 256, 0, st>>>(emb, D, start, B, out_ids, out_ld, finished, step_ptr, n_unfinished, ticket, x);
+                        int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
+                        const int64_t* forced, int forced_ld) {
+  decode_init_kernel<<<B, 256, 0, st>>>(emb, D, start, B, out_ids, out_ld, finished, step_ptr, n_unfinished, ticket, x,
+                                        forced, forced_ld);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 

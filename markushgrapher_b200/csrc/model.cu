@@ -255,7 +255,7 @@ struct mg_model {
   void vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_t* ids, const float* bbox, const float* px,
                    const int64_t* amask);
   void generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len, float* step_logits,
-                int32_t* steps_run);
+                int32_t* steps_run, const int64_t* forced = nullptr, int forced_ld = 0);
 };
 
 // ================================================================================================= finalize
@@ -678,7 +678,7 @@ void mg_model::encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const 
 
 // ================================================================================================= greedy decode
 void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len,
-                        float* step_logits, int32_t* steps_run) {
+                        float* step_logits, int32_t* steps_run, const int64_t* forced, int forced_ld) {
   const mg_config& c = cfg;
   MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
   MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
@@ -733,7 +733,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   int* finished = a.get<int>(B);
   int* ctr = a.get<int>(8);  // [0]=step [1]=n_unfinished [2]=ticket
   int64_t* ids_dev = out_ids;
-  launch_decode_init(st, shared, d, c.decoder_start_token_id, B, ids_dev, max_length, finished, ctr, ctr + 1, ctr + 2, x);
+  launch_decode_init(st, shared, d, c.decoder_start_token_id, B, ids_dev, max_length, finished, ctr, ctr + 1, ctr + 2, x,
+                     forced, forced_ld);
   ++launches;
   // split-K accumulation buffers start at zero; afterwards each is re-zeroed by a later kernel of the chain
   MG_CHECK_CUDA(cudaMemsetAsync(qkv, 0, sizeof(float) * (size_t)B * 3 * d, st));
@@ -770,7 +771,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     // final RMSNorm * d_model^-0.5 fused into the LM head (modeling_udop.py:1585-1590), direct store
     lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true);
     launch_greedy_select(st, logits, B, V, Vld, shared, d, c.eos_token_id, c.pad_token_id, ids_dev, max_length,
-                         finished, ctr, ctr + 1, ctr + 2, x, step_logits, (int64_t)(max_length - 1) * V, V);
+                         finished, ctr, ctr + 1, ctr + 2, x, step_logits, (int64_t)(max_length - 1) * V, V, forced,
+                         forced_ld);
     launches += 1;
   };
 
@@ -930,6 +932,27 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_encode_ms, m->ev[0], m->ev[1]));
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_decode_ms, m->ev[1], m->ev[2]));
   m->last_launches = m->launches - l0;
+  MG_API_END
+}
+
+int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                      const float* pixel_values, const int64_t* attn_mask, const int64_t* decoder_input_ids, int T,
+                      float* logits) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values && decoder_input_ids && logits, "null argument");
+  MG_REQUIRE(T >= 1, "empty decoder input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr || st == cudaStreamLegacy) {
+    MG_CHECK_CUDA(cudaDeviceSynchronize());
+    if (!m->own_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    st = m->own_stream;
+  }
+  m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
+  // teacher forcing through the cached decode path: step t consumes decoder_input_ids[:, t] and its logits are
+  // position t of the (B, T, V) output; T steps == max_length T+1
+  int64_t* ids_scratch = m->persist.get<int64_t>((int64_t)B * (T + 1));
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[3], st));
+  m->generate(st, B, T + 1, ids_scratch, nullptr, logits, nullptr, decoder_input_ids, T);
   MG_API_END
 }
 

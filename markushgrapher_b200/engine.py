@@ -176,6 +176,21 @@ class MGEngine:
             out = out[:, : _stop_column(out, lens, max_length)]
         return out
 
+    def forward_logits(self, input_ids, bbox, pixel_values, decoder_input_ids, attention_mask=None):
+        """teacher-forced logits (B, T, vocab) for decoder_input_ids (B, T) — `model(**batch).logits`"""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
+        dec = decoder_input_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        T = dec.shape[1]
+        logits = torch.empty((B, T, self.cfg.vocab_size), device=self.device, dtype=torch.float32)
+        L = _lib.lib()
+        L.mg_forward_logits.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] +
+                                        [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p])
+        with torch.cuda.device(self.device):
+            rc = L.mg_forward_logits(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px),
+                                     _lib.ptr(am), _lib.ptr(dec), T, _lib.ptr(logits))
+        _lib.check(rc, "mg_forward_logits")
+        return logits
+
     def profile_cross_attn(self, reps: int = 3):
         L = _lib.lib()
         L.mg_profile_cross_attn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3

@@ -1,0 +1,146 @@
+"""Host-side mirrors of the fork's image processor / tokenizer / processor classes (reference begin.py:105-111,
+utils/common.py:34-42). CPU-side input packing only — the tensors they emit are the hot path's input contract:
+input_ids (1,Lt) i64, bbox (1,Lt,4) f32 in [0,1], attention_mask (1,Lt), pixel_values (1,3,512,512) f32."""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+
+class MarkushgrapherImageProcessor:
+    def __init__(self, apply_ocr: bool = False, size=None, image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5), **kw):
+        if apply_ocr:
+            raise ValueError("apply_ocr=True (pytesseract) is not part of the hot path; OCR comes from ChemicalOCR")
+        size = size or {"height": 512, "width": 512}
+        self.size = (int(size["height"]), int(size["width"]))
+        self.mean = torch.tensor(image_mean).view(3, 1, 1)
+        self.std = torch.tensor(image_std).view(3, 1, 1)
+
+    def __call__(self, images, return_tensors="pt", **kw):
+        from PIL import Image
+
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        out = []
+        for im in images:
+            im = im.convert("RGB").resize((self.size[1], self.size[0]), resample=Image.BILINEAR)
+            t = torch.from_numpy(np.asarray(im, dtype=np.uint8).copy()).permute(2, 0, 1).float() * (1.0 / 255.0)
+            out.append((t - self.mean) / self.std)
+        return {"pixel_values": torch.stack(out)}
+
+
+class MarkushgrapherTokenizer:
+    """SentencePiece (T5/UDOP vocabulary) wrapper with the handful of methods markushgrapher.core calls
+    (markush_tokenizer.py:309-618, utils/common.py:47-64). EOS=1, PAD=0, vocab 33201."""
+
+    def __init__(self, sp_model_path: str, vocab_size: int = 33201, extra_ids: int = 100, loc_extra_ids: int = 501,
+                 other_extra_ids: int = 200):
+        import sentencepiece as spm
+
+        self.sp = spm.SentencePieceProcessor()
+        self.sp.Load(sp_model_path)
+        self.vocab_size = vocab_size
+        self.eos_token_id, self.pad_token_id, self.unk_token_id = 1, 0, 2
+        self.eos_token, self.pad_token = "</s>", "<pad>"
+        n = self.sp.GetPieceSize()
+        self.special = {}
+        # UDOP appends <extra_id_*>, <extra_l_id_*>, </extra_l_id_*>, <extra_t_id_*>, </extra_t_id_*>, <loc_*>, <other_*>
+        # after the sentencepiece vocabulary; ids are assigned in reverse order like the stock tokenizer
+        names = ([f"<extra_id_{i}>" for i in range(extra_ids - 1, -1, -1)] +
+                 [f"<extra_l_id_{i}>" for i in range(extra_ids - 1, -1, -1)] +
+                 [f"</extra_l_id_{i}>" for i in range(extra_ids - 1, -1, -1)] +
+                 [f"<extra_t_id_{i}>" for i in range(extra_ids - 1, -1, -1)] +
+                 [f"</extra_t_id_{i}>" for i in range(extra_ids - 1, -1, -1)] +
+                 [f"<loc_{i}>" for i in range(loc_extra_ids - 1, -1, -1)] +
+                 [f"<other_{i}>" for i in range(other_extra_ids - 1, -1, -1)])
+        for i, s in enumerate(names):
+            self.special[s] = n + i
+        self.special_inv = {v: k for k, v in self.special.items()}
+
+    @classmethod
+    def from_pretrained(cls, path: str, **kw):
+        fn = os.path.join(path, "spiece.model") if os.path.isdir(path) else path
+        if not os.path.exists(fn):
+            raise FileNotFoundError(f"{fn} not found: MarkushgrapherTokenizer needs the UDOP sentencepiece model")
+        return cls(fn, **kw)
+
+    def __len__(self):
+        return self.vocab_size
+
+    def tokenize(self, text: str) -> List[str]:
+        return self.sp.EncodeAsPieces(text)
+
+    def _convert_token_to_id(self, token: str) -> int:
+        return self.special.get(token, self.sp.PieceToId(token))
+
+    def convert_tokens_to_ids(self, tokens):
+        if isinstance(tokens, str):
+            return self._convert_token_to_id(tokens)
+        return [self._convert_token_to_id(t) for t in tokens]
+
+    def convert_ids_to_tokens(self, ids):
+        if isinstance(ids, int):
+            return self.special_inv.get(ids) or self.sp.IdToPiece(ids)
+        return [self.convert_ids_to_tokens(int(i)) for i in ids]
+
+    def encode(self, text: str, add_special_tokens: bool = True, **kw) -> List[int]:
+        ids = self.convert_tokens_to_ids(self.tokenize(text))
+        return ids + [self.eos_token_id] if add_special_tokens else ids
+
+    def decode(self, ids, skip_special_tokens: bool = False, **kw) -> str:
+        ids = [int(i) for i in (ids.tolist() if hasattr(ids, "tolist") else ids)]
+        out, cur = [], []
+        for i in ids:
+            if i in self.special_inv or i in (0, 1):
+                if cur:
+                    out.append(self.sp.DecodeIds(cur))
+                    cur = []
+                if not skip_special_tokens:
+                    out.append(self.special_inv.get(i, "</s>" if i == 1 else "<pad>"))
+            else:
+                cur.append(i)
+        if cur:
+            out.append(self.sp.DecodeIds(cur))
+        return "".join(out)
+
+
+class MarkushgrapherProcessor:
+    """processor(images=PIL, text=[prompt], text_pair=[[word,...]], boxes=[[[x0,y0,x1,y1],...]], return_tensors="pt")
+    -> input_ids, bbox, attention_mask, pixel_values with leading batch dim 1 (reference utils/common.py:34-42,68-71).
+    Prompt tokens and separators get box `sep_box`/zeros like the UDOP tokenizer (boxes are already normalised to
+    [0,1] by the reference's data pipeline, `normalize_bbox: True` in predict.yaml)."""
+
+    def __init__(self, image_processor: MarkushgrapherImageProcessor, tokenizer: MarkushgrapherTokenizer,
+                 sep_box=(1.0, 1.0, 1.0, 1.0)):
+        self.image_processor = image_processor
+        self.tokenizer = tokenizer
+        self.sep_box = list(sep_box)
+
+    def __call__(self, images=None, text=None, text_pair=None, boxes=None, return_tensors="pt", padding=False,
+                 truncation=False, max_length: Optional[int] = None, **kw):
+        tk = self.tokenizer
+        ids, bb = [], []
+        prompt = text[0] if isinstance(text, (list, tuple)) else text
+        for t in tk.encode(prompt, add_special_tokens=False):
+            ids.append(t)
+            bb.append([0.0, 0.0, 0.0, 0.0])
+        ids.append(tk.eos_token_id)
+        bb.append(self.sep_box)
+        words = text_pair[0] if text_pair and isinstance(text_pair[0], (list, tuple)) else (text_pair or [])
+        wboxes = boxes[0] if boxes and boxes[0] and isinstance(boxes[0][0], (list, tuple)) else (boxes or [])
+        for w, b in zip(words, wboxes):
+            for t in tk.encode(w, add_special_tokens=False):
+                ids.append(t)
+                bb.append([float(v) for v in b])
+        ids.append(tk.eos_token_id)
+        bb.append(self.sep_box)
+        if truncation and max_length:
+            ids, bb = ids[:max_length], bb[:max_length]
+        out = {"input_ids": torch.tensor([ids], dtype=torch.long), "bbox": torch.tensor([bb], dtype=torch.float32),
+               "attention_mask": torch.ones(1, len(ids), dtype=torch.long)}
+        if images is not None:
+            out.update(self.image_processor(images))
+        return out

@@ -64,3 +64,29 @@ def test_generate_host_path(pair):
     ids = eng.generate_host(**{k: v.pin_memory() for k, v in inp.items()}, max_length=16)
     assert not ids.is_cuda
     assert torch.equal(ids, ids_ref)
+
+
+def test_drop_in_model_class_generate_and_logits():
+    """the reference-facing object (MarkushgrapherForConditionalGeneration) end to end: generate() as called at
+    utils_evaluation.py:279-285 and model(**batch).logits as called at curriculumTrainer.py:655"""
+    from markushgrapher_b200.configuration import MarkushgrapherConfig
+    from markushgrapher_b200.modeling import MarkushgrapherForConditionalGeneration
+
+    cfg = O.MGConfig.tiny()
+    oracle = O.build(cfg, seed=0)
+    model = MarkushgrapherForConditionalGeneration(MarkushgrapherConfig.from_dims(cfg))
+    assert model.safe_load(model, oracle.export_state()) == []
+    model = model.to("cuda")
+    inp = O.make_inputs(cfg, 2, 12, seed=31)
+    enc = {k: v.to("cuda") for k, v in inp.items()}
+    labels = torch.randint(3, cfg.vocab_size, (2, 9))
+    ids = model.generate(**enc, labels=labels.to("cuda"), num_beams=1, max_length=14)
+    ids_ref = oracle.generate_greedy(**inp, max_length=14)
+    assert torch.equal(ids.cpu(), ids_ref)
+    labels[1, 6:] = -100
+    out = model(**enc, labels=labels.to("cuda"))
+    ref = oracle.forward_logits(inp["input_ids"], inp["bbox"], inp["pixel_values"], labels, inp["attention_mask"])
+    assert out.logits.shape == ref.shape
+    assert rel_err(out.logits, ref) < 1e-4
+    ref_loss = torch.nn.functional.cross_entropy(ref.view(-1, ref.shape[-1]), labels.view(-1), ignore_index=-100)
+    assert abs(out.loss.item() - ref_loss.item()) < 1e-3
