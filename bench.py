@@ -201,12 +201,14 @@ def run_ours(args):
     del state
     torch.cuda.empty_cache()
 
+    if world > 1:
+        eng.comm_init_from_torch()  # NCCL communicator owned by the library: per-step all-gather of token ids
     B = args.batch
     host = synth_inputs(cfg.image_size, B, TEXT_LEN, seed=1234 + rank, vocab=cfg.vocab_size)
     host = {k: v.pin_memory() for k, v in host.items()}
     devin = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = B * args.max_length * 8
+    d2h = B * args.max_length * 8 * world
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,18 +216,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gen_dev():
+        if world > 1:
+            return eng.generate_dist(**devin, max_length=args.max_length)
+        return eng.generate(**devin, max_length=args.max_length, trim=False)
+
+    def gen_host():
+        if world > 1:  # host shard -> device, sharded generate with per-step id exchange, all ids back to the host
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            return eng.generate_dist(**d, max_length=args.max_length).cpu()
+        return eng.generate_host(**host, max_length=args.max_length, trim=False)
+
     stream = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local)
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            eng.generate(**devin, max_length=args.max_length, trim=False)
+            gen_dev()
         barrier()
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         enc_ms, dec_ms, kernels = [], [], 0
         for _ in range(args.steps):
-            eng.generate(**devin, max_length=args.max_length, trim=False)
+            gen_dev()
             s = eng.last_stats()
             enc_ms.append(s["encode_ms"])
             dec_ms.append(s["decode_ms"])
@@ -234,13 +247,13 @@ def run_ours(args):
         barrier()
         ms_dev = ev0.elapsed_time(ev1)
         # ---- e2e: host buffers through the public host entry, copies inside the timed region
-        eng.generate_host(**host, max_length=args.max_length, trim=False)
+        gen_host()
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            ids = eng.generate_host(**host, max_length=args.max_length, trim=False)
+            ids = gen_host()
         e1.record(stream)
         barrier()
         ms_e2e_dev = e0.elapsed_time(e1)
@@ -273,7 +286,9 @@ def run_ours(args):
             "config": {"workload": f"configs[1]: batch-{B} synthetic 512x512 images per GPU, random-init "
                                    f"MarkushGrapher-2 dims (831M params), greedy <={args.max_length} tok",
                        "images_per_gpu": B, "text_len": TEXT_LEN, "max_length": args.max_length,
-                       "decode_steps_run": steps_run, "parallelism": f"image-batch sharding x{world}",
+                       "decode_steps_run": steps_run,
+                       "parallelism": f"image-batch sharding x{world}" + (
+                           ", ncclAllGather of token ids per decode step" if world > 1 else ""),
                        "l2": "inputs larger than L2 (cross-KV working set {:.1f} GB per step)".format(
                            B * L * 2 * M * d * 4 / 1e9)},
             "clocks": clocks,

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   __shared__ float s_bcast[2];
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x;
+  griddep_launch();
+  griddep_wait();
   const int step = SELF ? *step_ptr : 0;
   const int nk = SELF ? step + 1 : n_keys_cross;
   const int ncache = SELF ? step : nk;  // keys already resident in the caches
@@ -153,10 +155,8 @@ void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D
                           const float* dec_bias, const int* lut, float* ctx) {
   MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
   dim3 grid(H, B);
-  dec_attn_kernel<true><<<grid, 256, dec_attn_smem(max_keys), st>>>(qkv, 3 * D, kt, kt_ld, kt_bs, v, v_ld, v_bs,
-                                                                     step_ptr, 0, nullptr, 0, dec_bias, lut, H, D,
-                                                                     ctx);
-  MG_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(dec_attn_kernel<true>, grid, dim3(256), dec_attn_smem(max_keys), st, qkv, 3 * D, kt, kt_ld, kt_bs, v, v_ld,
+             v_bs, step_ptr, 0, (const int*)nullptr, 0, dec_bias, lut, H, D, ctx);
 }
 
 void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __r
   constexpr int VR = CA_STAGE_BYTES / (HD * 4);  // keys per V chunk
   const int nvc = (Mp + VR - 1) / VR;
 
+  griddep_launch();
   if (tid == 0) {
     for (int s = 0; s < CA_NST; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -214,8 +215,14 @@ __global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __r
     }
     fence_mbar_init();
   }
-  if (tid < HD) sq[tid] = q[(int64_t)b * D + h * HD + tid];
   __syncthreads();
+  // The cross K/V blocks were written once before the decode loop, so the producer starts streaming them right
+  // away; only the consumers depend on the preceding kernel (q) and wait for it.
+  if (warp != 8) {
+    griddep_wait();
+    if (tid < HD) sq[tid] = q[(int64_t)b * D + h * HD + tid];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
 
   if (warp == 8) {
     // ------------------------------------------------------------------ producer
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(288) cross_attn_stream_kernel(const float* __r
         if (++s == CA_NST) { s = 0; ph ^= 1; }
       }
     }
+    griddep_wait();  // every thread of every kernel in the chain waits once: keeps completion order transitive
     return;
   }
   // -------------------------------------------------------------------- consumers (256 threads)
@@ -340,8 +348,7 @@ void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int
     attr = true;
   }
   dim3 grid(H, B);
-  cross_attn_stream_kernel<<<grid, 288, smem, st>>>(q, kt, v, mask, Mp, H, D, ctx);
-  MG_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(cross_attn_stream_kernel, grid, dim3(288), smem, st, q, kt, v, mask, Mp, H, D, ctx);
 }
 
 // =====================================================================================================
@@ -372,8 +379,11 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
                                                             int* __restrict__ n_unfinished, int* __restrict__ ticket,
                                                             float* __restrict__ x_next, float* __restrict__ logits_dump,
                                                             int64_t dump_bs, int64_t dump_ss,
-                                                            const int64_t* __restrict__ forced, int forced_ld) {
+                                                            const int64_t* __restrict__ forced, int forced_ld,
+                                                            int* __restrict__ step_tok) {
   const int b = blockIdx.x;
+  griddep_launch();
+  griddep_wait();
   const float* lg = logits + (int64_t)b * ld;
   const int step = *step_ptr;
   float best = -INFINITY;
@@ -412,6 +422,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
     const int fin = finished[b];
     int tok = fin ? pad : bi;
     out_ids[(int64_t)b * out_ld + step + 1] = tok;
+    if (step_tok) step_tok[b] = tok;
     if (forced) {
       // teacher forcing (model(**batch).logits): the next decoder input is given, nothing ever "finishes"
       tok = (int)forced[(int64_t)b * forced_ld + min(step + 1, forced_ld - 1)];
@@ -440,11 +451,10 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
 void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
-                          int64_t dump_ss, const int64_t* forced, int forced_ld) {
-  greedy_select_kernel<<<B, 256, 0, st>>>(logits, V, ld, emb, D, eos, pad, out_ids, out_ld, finished, step_ptr,
-                                          n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss, forced,
-                                          forced_ld);
-  MG_CHECK_CUDA(cudaGetLastError());
+                          int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok) {
+  launch_pdl(greedy_select_kernel, dim3(B), dim3(256), (size_t)0, st, logits, V, ld, emb, D, eos, pad, out_ids, out_ld,
+             finished, step_ptr, n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss, forced, forced_ld,
+             step_tok);
 }
 
 // decode state reset: ids[:,0] = start token, x = emb[start], finished = 0, step = 0
@@ -486,6 +496,27 @@ __global__ void out_len_kernel(const int64_t* __restrict__ ids, int B, int ld, i
 }
 void launch_out_len(cudaStream_t st, const int64_t* ids, int B, int ld, int ncols, int eos, int* len) {
   out_len_kernel<<<(B + 127) / 128, 128, 0, st>>>(ids, B, ld, ncols, eos, len);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// After the per-step all-gather: gathered[r][b] = token rank r emitted for its image b at column `col`.
+// Writes the global id matrix and maintains the global finished flags / unfinished count (same stop rule on all ranks).
+__global__ void scatter_step_kernel(const int* __restrict__ gathered, int n_rows, int col, int ld, int eos,
+                                    int64_t* __restrict__ all_ids, int* __restrict__ gfinished,
+                                    int* __restrict__ g_unfinished) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int tok = gathered[i];
+  all_ids[(int64_t)i * ld + col] = tok;
+  if (!gfinished[i] && tok == eos) {
+    gfinished[i] = 1;
+    atomicSub(g_unfinished, 1);
+  }
+}
+void launch_scatter_step(cudaStream_t st, const int* gathered, int n_rows, int col, int ld, int eos, int64_t* all_ids,
+                         int* gfinished, int* g_unfinished) {
+  scatter_step_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(gathered, n_rows, col, ld, eos, all_ids, gfinished,
+                                                          g_unfinished);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 

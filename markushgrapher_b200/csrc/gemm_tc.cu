@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant
   const int m0 = blockIdx.x * BM;
   const int kb0 = blockIdx.y * p.kb_per_cta;
   const int kb1 = min(p.num_kb, kb0 + p.kb_per_cta);
+  griddep_launch();  // the next kernel may start prefetching its own weights now
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tw_hi);
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant
   } else {
     // ---------------------------------------------------------------- workers (warps 2..5, 128 threads)
     const int t = threadIdx.x - 64;
+    griddep_wait();  // everything below reads / accumulates into buffers owned by the preceding kernels
     {  // activation tiles for every k-block of this CTA, G k-blocks per round trip to L2
       constexpr int NI = (R * 16) / 128;  // float4 items per thread per k-block
       constexpr int G = 4 / NG;           // k-blocks whose loads are issued together
@@ -612,8 +614,7 @@ static void launch_skinny_ng(cudaStream_t st, const SkinnyParams& p, dim3 grid) 
     MG_CHECK_CUDA(cudaFuncSetAttribute(skinny_tc_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_smem = 200 * 1024;
   }
-  skinny_tc_kernel<NG><<<grid, 192, smem, st>>>(p);
-  MG_CHECK_CUDA(cudaGetLastError());
+  launch_pdl(skinny_tc_kernel<NG>, grid, dim3(192), (size_t)smem, st, p);
 }
 
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
@@ -636,7 +637,8 @@ void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes 
   if (!store) ksplit = std::min(p.num_kb, std::max(1, 148 / tiles));
   p.kb_per_cta = (p.num_kb + ksplit - 1) / ksplit;
   ksplit = (p.num_kb + p.kb_per_cta - 1) / p.kb_per_cta;
-  p.stages = std::min(4, p.kb_per_cta);
+  static const int max_stages = getenv("MG_SKINNY_STAGES") ? atoi(getenv("MG_SKINNY_STAGES")) : 2;
+  p.stages = std::min(max_stages, p.kb_per_cta);  // <= 84 KB: CTAs of consecutive (PDL-overlapped) kernels co-reside
   p.pro = pro; p.lnw = lnw; p.eps = eps; p.scale = scale;
   p.zero_ptr = zero_ptr; p.zero_n = zero_n; p.store = store ? 1 : 0;
   dim3 grid(tiles, ksplit);

@@ -44,7 +44,9 @@ void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
 void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
-                          int64_t dump_ss, const int64_t* forced, int forced_ld);
+                          int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok);
+void launch_scatter_step(cudaStream_t st, const int* gathered, int n_rows, int col, int ld, int eos, int64_t* all_ids,
+                         int* gfinished, int* g_unfinished);
 void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int B, int64_t* out_ids, int out_ld,
                         int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
                         const int64_t* forced, int forced_ld);

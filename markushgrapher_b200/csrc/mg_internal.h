@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <stdexcept>
 #include <string>
 
@@ -80,5 +82,24 @@ void launch_gemm(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, in
 // fp32 [rows, cols] (row stride ld_in) -> planes [rows, ld_out], zero-filling cols..ld_out
 void launch_split(cudaStream_t st, const float* in, int64_t rows, int64_t cols, int64_t ld_in, Planes out,
                   int64_t ld_out);
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may begin while its predecessor
+// in the stream is still running and MUST call griddep_wait() before touching anything the predecessor produces
+// (or still reads). Captured into CUDA graphs as programmatic dependency edges.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  static const bool pdl_on = !(getenv("MG_NO_PDL") && getenv("MG_NO_PDL")[0] == '1');  // A/B switch for profiling
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_on ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
 
 }  // namespace mg

@@ -3,7 +3,9 @@
 //   * the fork's Markushgrapher encoder forward (Swin branch + projector + UdopStack encoder + fusion concat;
 //     stock restatement transformers/models/udop/modeling_udop.py:1064-1256, models/swin/modeling_swin.py:534-913),
 //   * GenerationMixin.generate / _sample (transformers/generation/utils.py:2131, 2658-2842) for greedy decode.
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>
 #include <string.h>
 
 #include <algorithm>
@@ -22,6 +24,40 @@ int set_error(const Error& e);
 int set_error(const std::exception& e);
 
 static inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// NCCL is resolved at run time (dlopen of the libnccl.so.2 already loaded by torch, else the system one) so the
+// library has no link-time dependency on it; only the multi-GPU entry points touch it.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool loaded = false;
+  if (!loaded) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    MG_REQUIRE(h != nullptr, std::string("cannot load libnccl.so.2: ") + dlerror());
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    MG_REQUIRE(api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy, "libnccl lacks a required symbol");
+    loaded = true;
+  }
+  return api;
+}
+#define MG_CHECK_NCCL(expr)                                                                                  \
+  do {                                                                                                       \
+    ncclResult_t _r = (expr);                                                                                \
+    if (_r != ncclSuccess)                                                                                   \
+      throw mg::Error(-5, std::string(#expr) + " failed: " +                                                 \
+                              (nccl_api().GetErrorString ? nccl_api().GetErrorString(_r) : "nccl error"));   \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------ memory
 // Chunked bump allocator: deterministic allocation sequences reuse the same addresses after reset().
@@ -145,6 +181,10 @@ struct mg_model {
   int* pinned_flag = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t own_stream = nullptr;
+  // multi-GPU (image-batch sharding): one NCCL all-gather of the step's token ids per decode step
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+  int64_t* dist_all_ids = nullptr;  // (world*B, max_length) on every rank, set per call
   // buffers of the last generate call (valid until the next encode/generate), for mg_profile_cross_attn
   std::vector<float*> prof_ckt, prof_cv;
   float* prof_q = nullptr;
@@ -156,6 +196,7 @@ struct mg_model {
     scratch.release();
     if (pinned_flag) cudaFreeHost(pinned_flag);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (comm) nccl_api().CommDestroy(comm);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
   }
@@ -228,6 +269,15 @@ struct mg_model {
     return p;
   }
 
+  int64_t* ids_buf = nullptr;
+  int64_t ids_cap = 0;
+  int64_t* persist_ids(int64_t n) {  // scratch for local ids of mg_generate_dist (kept across calls)
+    if (n > ids_cap) {
+      ids_buf = own<int64_t>(n);
+      ids_cap = n;
+    }
+    return ids_buf;
+  }
   Planes planes(Arena& a, int64_t n) {
     Planes p;
     p.hi = a.get<bf16>(n);
@@ -731,7 +781,28 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   float* hbuf = a.get<float>((int64_t)B * c.d_ff);
   float* logits = a.get<float>((int64_t)B * Vld);
   int* finished = a.get<int>(B);
-  int* ctr = a.get<int>(8);  // [0]=step [1]=n_unfinished [2]=ticket
+  int* ctr = a.get<int>(8);  // [0]=step [1]=n_unfinished [2]=ticket [3]=global n_unfinished
+  const bool dist = comm != nullptr && dist_all_ids != nullptr && forced == nullptr;
+  int* step_tok = a.get<int>(B);
+  int* gathered = a.get<int>((int64_t)world * B);
+  int* gfinished = a.get<int>((int64_t)world * B);
+  if (dist) {
+    MG_CHECK_CUDA(cudaMemsetAsync(gfinished, 0, sizeof(int) * (size_t)world * B, st));
+    MG_CHECK_CUDA(cudaMemsetAsync(dist_all_ids, 0, sizeof(int64_t) * (size_t)world * B * max_length, st));
+    // column 0 of every row = decoder start id; the global unfinished counter starts at world*B
+    std::vector<int64_t> col0((size_t)world * B, (int64_t)c.decoder_start_token_id);
+    MG_CHECK_CUDA(cudaMemcpy2DAsync(dist_all_ids, sizeof(int64_t) * max_length, col0.data(), sizeof(int64_t),
+                                    sizeof(int64_t), (size_t)world * B, cudaMemcpyHostToDevice, st));
+    const int wb = world * B;
+    MG_CHECK_CUDA(cudaMemcpyAsync(ctr + 3, &wb, sizeof(int), cudaMemcpyHostToDevice, st));
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));  // col0 / wb are host temporaries
+  }
+  // exchange of one decode step: every rank learns every image's new token and applies the same stop rule
+  auto exchange = [&](int col) {
+    MG_CHECK_NCCL(nccl_api().AllGather(step_tok, gathered, (size_t)B, ncclInt32, comm, st));
+    launch_scatter_step(st, gathered, world * B, col, max_length, c.eos_token_id, dist_all_ids, gfinished, ctr + 3);
+    launches += 2;
+  };
   int64_t* ids_dev = out_ids;
   launch_decode_init(st, shared, d, c.decoder_start_token_id, B, ids_dev, max_length, finished, ctr, ctr + 1, ctr + 2, x,
                      forced, forced_ld);
@@ -772,7 +843,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true);
     launch_greedy_select(st, logits, B, V, Vld, shared, d, c.eos_token_id, c.pad_token_id, ids_dev, max_length,
                          finished, ctr, ctr + 1, ctr + 2, x, step_logits, (int64_t)(max_length - 1) * V, V, forced,
-                         forced_ld);
+                         forced_ld, step_tok);
     launches += 1;
   };
 
@@ -785,6 +856,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   // step 0 runs eagerly (lazy one-time initialisation happens outside graph capture) ...
   one_step();
   done_steps = 1;
+  if (dist) exchange(1);
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   const int64_t per_step = launches;
@@ -801,20 +873,24 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     }
     MG_CHECK_CUDA(cudaStreamEndCapture(st, &graph));
     MG_CHECK_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    if (getenv("MG_DUMP_GRAPH")) cudaGraphDebugDotPrint(graph, getenv("MG_DUMP_GRAPH"), 0);
     const int64_t step_launches = launches - before;
     launches = before;
-    pinned_flag[0] = B;
+    pinned_flag[0] = dist ? world * B : B;
     const int check_every = 16;
     bool stop = false;
     while (done_steps < total_steps && !stop) {
       const int n = std::min(check_every, total_steps - done_steps);
-      for (int i = 0; i < n; ++i) MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+      for (int i = 0; i < n; ++i) {
+        MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+        if (dist) exchange(done_steps + i + 1);
+      }
       launches += step_launches * n;
       done_steps += n;
       // poll the "all finished" counter one window late so the GPU never drains
       MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));
       if (pinned_flag[0] == 0) stop = true;
-      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? ctr + 3 : ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
       MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
     }
   }
@@ -932,6 +1008,42 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_encode_ms, m->ev[0], m->ev[1]));
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_decode_ms, m->ev[1], m->ev[2]));
   m->last_launches = m->launches - l0;
+  MG_API_END
+}
+
+int mg_nccl_unique_id(void* out_128_bytes) {
+  MG_API_BEGIN
+  MG_REQUIRE(out_128_bytes, "null argument");
+  ncclUniqueId id;
+  MG_CHECK_NCCL(nccl_api().GetUniqueId(&id));
+  memcpy(out_128_bytes, &id, sizeof(id));
+  MG_API_END
+}
+
+int mg_comm_init(mg_model* m, int world, int rank, const void* id_128_bytes) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && id_128_bytes && world >= 1 && rank >= 0 && rank < world, "bad arguments");
+  MG_REQUIRE(m->comm == nullptr, "communicator already initialised");
+  ncclUniqueId id;
+  memcpy(&id, id_128_bytes, sizeof(id));
+  MG_CHECK_NCCL(nccl_api().CommInitRank(&m->comm, world, id, rank));
+  m->world = world;
+  m->rank = rank;
+  MG_API_END
+}
+
+int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64_t* input_ids, const float* bbox,
+                     const float* pixel_values, const int64_t* attn_mask, int max_length, int64_t* all_ids,
+                     int32_t* steps_run) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && m->comm, "mg_comm_init has not been called");
+  MG_REQUIRE(all_ids, "null argument");
+  int64_t* local = m->persist_ids((int64_t)B_local * max_length);
+  m->dist_all_ids = all_ids;
+  int rc = mg_generate(m, stream, B_local, Lt, input_ids, bbox, pixel_values, attn_mask, 1, max_length, local, nullptr,
+                       nullptr, steps_run);
+  m->dist_all_ids = nullptr;
+  if (rc != 0) return rc;
   MG_API_END
 }
 

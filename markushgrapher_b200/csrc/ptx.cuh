@@ -149,6 +149,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24);// m_dim
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// griddep_wait(): block until the preceding kernel in the stream has completed and its writes are visible.
+// griddep_launch(): allow the next kernel (launched with the programmatic-serialization attribute) to start its
+// independent prologue (barrier init, TMEM alloc, weight / KV prefetch) while this one is still running.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

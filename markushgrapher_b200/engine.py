@@ -176,6 +176,38 @@ class MGEngine:
             out = out[:, : _stop_column(out, lens, max_length)]
         return out
 
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    def comm_init_from_torch(self, group=None):
+        """join an NCCL communicator owned by the library; the 128-byte id travels over torch.distributed"""
+        import torch.distributed as dist
+
+        L = _lib.lib()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(L.mg_nccl_unique_id(buf), "mg_nccl_unique_id")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        L.mg_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        with torch.cuda.device(self.device):
+            _lib.check(L.mg_comm_init(self._h, world, rank, box[0]), "mg_comm_init")
+        self.world, self.rank = world, rank
+
+    def generate_dist(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512):
+        """this rank's shard in, ids of the WHOLE batch (world*B_local, max_length) out, on every rank"""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
+        out = torch.empty((self.world * B, max_length), device=self.device, dtype=torch.int64)
+        steps = ctypes.c_int32(0)
+        L = _lib.lib()
+        L.mg_generate_dist.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] +
+                                       [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p])
+        with torch.cuda.device(self.device):
+            rc = L.mg_generate_dist(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px),
+                                    _lib.ptr(am), int(max_length), _lib.ptr(out), ctypes.addressof(steps))
+        _lib.check(rc, "mg_generate_dist")
+        self.last_steps = steps.value
+        return out
+
     def forward_logits(self, input_ids, bbox, pixel_values, decoder_input_ids, attention_mask=None):
         """teacher-forced logits (B, T, vocab) for decoder_input_ids (B, T) — `model(**batch).logits`"""
         ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
