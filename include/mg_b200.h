@@ -70,8 +70,10 @@ int mg_finalize(mg_model* m, void* stream);
 int mg_encode(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
               const float* pixel_values, const int64_t* attn_mask, float* enc_out, int32_t* enc_mask, int32_t* M_out);
 
-/* Greedy generate (num_beams must be 1 in this revision). out_ids (B, max_length) i64: column 0 = decoder start id,
- * finished rows padded with pad id. out_len (B) i32 = tokens up to and including EOS (or the columns generated).
+/* Generate: num_beams == 1 greedy (GenerationMixin._sample), 2..8 beam search (GenerationMixin._beam_search with
+ * the defaults the reference leaves in place: length_penalty 1.0, early_stopping False, 1 returned sequence).
+ * out_ids (B, max_length) i64: column 0 = decoder start id, finished rows padded with pad id.
+ * out_len (B) i32 = tokens up to and including EOS (or the columns generated).
  * step_logits: NULL or (B, max_length-1, vocab) f32 receiving the logits of every step (debug / parity).
  * steps_run (host, may be NULL): number of decode steps executed. Synchronises `stream` before returning. */
 int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,

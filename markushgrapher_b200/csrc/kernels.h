@@ -53,6 +53,32 @@ void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int
 
 void launch_out_len(cudaStream_t st, const int64_t* ids, int B, int ld, int ncols, int eos, int* len);
 
+// ---- beam.cu
+struct BeamState {
+  int64_t* run_seq;
+  int64_t* fin_seq;
+  float* run_score;
+  float* fin_score;
+  int* fin_flag;
+  int* fin_len;
+  int* unsat;
+  int* anc0;
+  int* anc1;
+  int* ctrl;
+  int64_t* tmp_seq;  // [B][nb][L] scratch for the slot permutations
+  int B, nb, L, anc_ld;
+};
+void launch_beam_self_attn(cudaStream_t st, const float* qkv, int R, int H, int D, float* kt, int64_t kt_ld,
+                           int64_t kt_bs, float* v, int64_t v_ld, int64_t v_bs, const int* step_ptr,
+                           const int* anc_sel, const int* anc0, const int* anc1, int anc_ld, const float* dec_bias,
+                           const int* lut, float* ctx);
+void launch_beam_cross_attn(cudaStream_t st, const float* q, int B, int nq, int H, int D, const float* kt,
+                            const float* v, int Mp, const int* mask, float* ctx);
+void launch_beam_init(cudaStream_t st, const BeamState& s, const float* emb, int D, int start, int pad, float* x);
+void launch_beam_select(cudaStream_t st, const BeamState& s, const float* logits, int V, int64_t ld, const float* emb,
+                        int D, int eos, int max_length, float* x_next);
+void launch_beam_finalize(cudaStream_t st, const BeamState& s, int pad, int64_t* out_ids, int* out_len);
+
 // gemm_tc.cu: tensor-core skinny linear with fused prologue (pro: 0 none, 1 RMSNorm, 2 ReLU), split-K atomics
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,

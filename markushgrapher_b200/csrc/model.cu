@@ -304,8 +304,11 @@ struct mg_model {
   void swin_forward(cudaStream_t st, int B0, int Bc, const float* px);
   void vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_t* ids, const float* bbox, const float* px,
                    const int64_t* amask);
+  void project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv);
   void generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len, float* step_logits,
                 int32_t* steps_run, const int64_t* forced = nullptr, int forced_ld = 0);
+  void generate_beam(cudaStream_t st, int B, int nb, int max_length, int64_t* out_ids, int32_t* out_len,
+                     int32_t* steps_run);
 };
 
 // ================================================================================================= finalize
@@ -726,20 +729,12 @@ void mg_model::encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const 
   ++launches;
 }
 
-// ================================================================================================= greedy decode
-void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len,
-                        float* step_logits, int32_t* steps_run, const int64_t* forced, int forced_ld) {
+// cross K^T / V of every decoder layer, once per generate (UdopAttention :575-583). K^T [B][H][64][Mp] via operand
+// swap, V head-major [B][H][Mp][64]: every (image, head) block is one contiguous stream for the decode kernels.
+void mg_model::project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv) {
   const mg_config& c = cfg;
-  MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
-  MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
-  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
+  const int d = c.d_model, H = c.num_heads, Mp = cur_Mp, NL = c.num_decoder_layers;
   Arena& a = scratch;
-  a.reset();
-  const int Tp = (int)rup(max_length, 4);
-  const int64_t Vld = rup(V, 4);
-
-  // ---- cross K^T / V for every layer (once per generate; UdopAttention :575-583)
-  std::vector<float*> ckt(NL), cv(NL);
   for (int l = 0; l < NL; ++l) {
     ckt[l] = a.get<float>((int64_t)B * d * Mp);
     cv[l] = a.get<float>((int64_t)B * Mp * d);
@@ -768,6 +763,22 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       ++launches;
     }
   }
+}
+
+// ================================================================================================= greedy decode
+void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len,
+                        float* step_logits, int32_t* steps_run, const int64_t* forced, int forced_ld) {
+  const mg_config& c = cfg;
+  MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
+  MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
+  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
+  Arena& a = scratch;
+  a.reset();
+  const int Tp = (int)rup(max_length, 4);
+  const int64_t Vld = rup(V, 4);
+
+  std::vector<float*> ckt(NL), cv(NL);
+  project_cross_kv(st, B, ckt, cv);
   // ---- decode state
   std::vector<float*> skt(NL), sv(NL);
   for (int l = 0; l < NL; ++l) {
@@ -905,6 +916,121 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   if (steps_run) *steps_run = done_steps;
 }
 
+// ================================================================================================= beam search
+void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int64_t* out_ids, int32_t* out_len,
+                             int32_t* steps_run) {
+  const mg_config& c = cfg;
+  MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
+  MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
+  MG_REQUIRE(nb >= 2 && nb <= 8, "2 <= num_beams <= 8");
+  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
+  const int R = B * nb;
+  Arena& a = scratch;
+  a.reset();
+  const int Tp = (int)rup(max_length, 4);
+  const int64_t Vld = rup(V, 4);
+  std::vector<float*> ckt(NL), cv(NL);
+  project_cross_kv(st, B, ckt, cv);
+  std::vector<float*> skt(NL), sv(NL);
+  for (int l = 0; l < NL; ++l) {
+    skt[l] = a.get<float>((int64_t)R * d * Tp);
+    sv[l] = a.get<float>((int64_t)R * Tp * d);
+  }
+  float* x = a.get<float>((int64_t)R * d);
+  float* qkv = a.get<float>((int64_t)R * 3 * d);
+  float* q = a.get<float>((int64_t)R * d);
+  float* ctx = a.get<float>((int64_t)R * d);
+  float* hbuf = a.get<float>((int64_t)R * c.d_ff);
+  float* logits = a.get<float>((int64_t)R * Vld);
+  BeamState bs;
+  bs.B = B; bs.nb = nb; bs.L = max_length; bs.anc_ld = Tp;
+  bs.run_seq = a.get<int64_t>((int64_t)R * max_length);
+  bs.fin_seq = a.get<int64_t>((int64_t)R * max_length);
+  bs.tmp_seq = a.get<int64_t>((int64_t)R * max_length);
+  bs.run_score = a.get<float>(R);
+  bs.fin_score = a.get<float>(R);
+  bs.fin_flag = a.get<int>(R);
+  bs.fin_len = a.get<int>(R);
+  bs.unsat = a.get<int>(B);
+  bs.anc0 = a.get<int>((int64_t)R * Tp);
+  bs.anc1 = a.get<int>((int64_t)R * Tp);
+  bs.ctrl = a.get<int>(8);
+  // fill value of unfinished tail positions: stock transformers computes `pad_token_id or eos_token_id[0]`
+  // (generation/utils.py:3165), i.e. EOS when the pad id is 0 as it is for UDOP/T5 -- mirrored for id parity
+  const int fill = c.pad_token_id != 0 ? c.pad_token_id : c.eos_token_id;
+  launch_beam_init(st, bs, shared, d, c.decoder_start_token_id, fill, x);
+  ++launches;
+  MG_CHECK_CUDA(cudaMemsetAsync(qkv, 0, sizeof(float) * (size_t)R * 3 * d, st));
+  MG_CHECK_CUDA(cudaMemsetAsync(q, 0, sizeof(float) * (size_t)R * d, st));
+  MG_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * (size_t)R * c.d_ff, st));
+
+  auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
+                 float scale, float* zp, int64_t zn, bool store) {
+    for (int b0 = 0; b0 < R; b0 += 128) {
+      const int bc = std::min(128, R - b0);
+      launch_skinny_tc(st, pro, xin + (int64_t)b0 * ldx, ldx, W.w, W.ldk, out + (int64_t)b0 * ld_out, ld_out, bc, W.N,
+                       W.K, lnw, c.ln_eps, scale, b0 == 0 ? zp : nullptr, zn, store);
+      ++launches;
+    }
+  };
+  auto one_step = [&]() {
+    for (int l = 0; l < NL; ++l) {
+      DecLayer& L = dec[l];
+      lin(1, x, d, L.qkv, qkv, 3 * d, L.ln1, 1.f, hbuf, (int64_t)R * c.d_ff, false);
+      launch_beam_self_attn(st, qkv, R, H, d, skt[l], Tp, (int64_t)d * Tp, sv[l], d, (int64_t)Tp * d, bs.ctrl,
+                            bs.ctrl + 1, bs.anc0, bs.anc1, Tp, dec_bias, lut_dec, ctx);
+      lin(0, ctx, d, L.o, x, d, nullptr, 1.f, nullptr, 0, false);
+      lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv, (int64_t)R * 3 * d, false);
+      launch_beam_cross_attn(st, q, B, nb, H, d, ckt[l], cv[l], Mp, mem_mask, ctx);
+      lin(0, ctx, d, L.co, x, d, nullptr, 1.f, nullptr, 0, false);
+      lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q, (int64_t)R * d, false);
+      lin(2, hbuf, c.d_ff, L.wo, x, d, nullptr, 1.f, nullptr, 0, false);
+      launches += 2;
+    }
+    lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true);
+    launch_beam_select(st, bs, logits, V, Vld, shared, d, c.eos_token_id, max_length, x);
+    launches += 1;
+  };
+  const int total_steps = max_length - 1;
+  one_step();
+  int done_steps = 1;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  if (total_steps > 1) {
+    const int64_t before = launches;
+    MG_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      one_step();
+    } catch (...) {
+      cudaGraph_t g2;
+      cudaStreamEndCapture(st, &g2);
+      throw;
+    }
+    MG_CHECK_CUDA(cudaStreamEndCapture(st, &graph));
+    MG_CHECK_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    const int64_t step_launches = launches - before;
+    launches = before;
+    pinned_flag[0] = 0;  // "done" flag of the device-side stop rule
+    bool stop = false;
+    while (done_steps < total_steps && !stop) {
+      const int n = std::min(16, total_steps - done_steps);
+      for (int i = 0; i < n; ++i) MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+      launches += step_launches * n;
+      done_steps += n;
+      MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));
+      if (pinned_flag[0] != 0) stop = true;
+      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, bs.ctrl + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
+    }
+  }
+  launch_beam_finalize(st, bs, fill, out_ids, out_len);
+  ++launches;
+  MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  if (steps_run) *steps_run = done_steps;
+}
+
 // ================================================================================================= C ABI
 #define MG_API_BEGIN try {
 #define MG_API_END                                        \
@@ -988,7 +1114,8 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
                 int32_t* out_len, float* step_logits, int32_t* steps_run) {
   MG_API_BEGIN
   MG_REQUIRE(m && input_ids && bbox && pixel_values && out_ids, "null argument");
-  MG_REQUIRE(num_beams == 1, "beam search is not implemented in this revision (num_beams must be 1)");
+  MG_REQUIRE(num_beams >= 1 && num_beams <= 8, "1 <= num_beams <= 8");
+  MG_REQUIRE(num_beams == 1 || step_logits == nullptr, "step_logits is only available for greedy decoding");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (st == nullptr || st == cudaStreamLegacy) {
     // the decode step is replayed from a captured CUDA graph and the legacy default stream cannot be
@@ -1002,7 +1129,10 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
   m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
   MG_CHECK_CUDA(cudaEventRecord(m->ev[1], st));
   MG_CHECK_CUDA(cudaEventRecord(m->ev[3], st));
-  m->generate(st, B, max_length, out_ids, out_len, step_logits, steps_run);
+  if (num_beams == 1)
+    m->generate(st, B, max_length, out_ids, out_len, step_logits, steps_run);
+  else
+    m->generate_beam(st, B, num_beams, max_length, out_ids, out_len, steps_run);
   MG_CHECK_CUDA(cudaEventRecord(m->ev[2], st));
   MG_CHECK_CUDA(cudaEventSynchronize(m->ev[2]));
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_encode_ms, m->ev[0], m->ev[1]));

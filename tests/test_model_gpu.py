@@ -90,3 +90,34 @@ def test_drop_in_model_class_generate_and_logits():
     assert rel_err(out.logits, ref) < 1e-4
     ref_loss = torch.nn.functional.cross_entropy(ref.view(-1, ref.shape[-1]), labels.view(-1), ignore_index=-100)
     assert abs(out.loss.item() - ref_loss.item()) < 1e-3
+
+
+@pytest.mark.parametrize("B,Lt,max_length,nb", [(2, 12, 20, 4), (3, 16, 28, 5), (1, 12, 16, 2)])
+def test_beam_search_token_identical(pair, B, Lt, max_length, nb):
+    """num_beams > 1 (the reference's predict.yaml default is beam_search: True -> 5 beams) against the stock
+    GenerationMixin._beam_search run on the oracle"""
+    cfg, oracle, eng = pair
+    inp = O.make_inputs(cfg, B, Lt, seed=40 + B + nb, ragged=(B == 3))
+    ref = oracle.hf_generate(**inp, max_length=max_length, num_beams=nb)
+    ids = eng.generate(**inp, max_length=max_length, num_beams=nb)
+    assert ids.shape == ref.shape, (ids.shape, ref.shape)
+    assert torch.equal(ids.cpu(), ref), (ids.cpu(), ref)
+
+
+def test_beam_search_with_early_eos(pair):
+    """make EOS likely so hypotheses finish at different lengths: exercises the finished-beam merge, the length
+    normalisation and the early-stop heuristic"""
+    cfg, oracle, eng0 = pair
+    import copy
+    o2 = copy.deepcopy(oracle)
+    with torch.no_grad():
+        o2.lm_head.weight[1] = o2.lm_head.weight[1] * 0.0 + o2.lm_head.weight[7] * 1.5 + o2.lm_head.weight[11] * 1.5
+    eng = MGEngine(cfg, o2.export_state())
+    inp = O.make_inputs(cfg, 4, 14, seed=77)
+    for nb in (3, 5):
+        ref = o2.hf_generate(**inp, max_length=40, num_beams=nb)
+        ids = eng.generate(**inp, max_length=40, num_beams=nb)
+        assert (ref == 1).any(), "test did not produce any EOS"
+        assert ids.shape == ref.shape, (ids.shape, ref.shape)
+        assert torch.equal(ids.cpu(), ref), (ids.cpu(), ref)
+    eng.close()
