@@ -126,6 +126,9 @@ def synth_inputs(image_size, batch, text_len, seed, vocab):
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
+_ORACLE = {}
+
+
 def cpu_reference_sample(sample_batch, sample_len, full_len, threads):
     """Times the CPU oracle (kind="port": stock-transformers restatement of the reference path) on a bounded
     sample and extrapolates the per-image time to a full `full_len`-token greedy decode of the same batch.
@@ -134,8 +137,11 @@ def cpu_reference_sample(sample_batch, sample_len, full_len, threads):
     from oracle import mg_oracle as O
 
     torch.set_num_threads(threads)
-    cfg = O.MGConfig.full()
-    model = O.build(cfg, seed=0)
+    if "model" not in _ORACLE:  # full-size random-init model, built once per process
+        cfg = O.MGConfig.full()
+        _ORACLE["cfg"] = cfg
+        _ORACLE["model"] = O.build(cfg, seed=0)
+    cfg, model = _ORACLE["cfg"], _ORACLE["model"]
     inp = O.make_inputs(cfg, sample_batch, TEXT_LEN, seed=1234)
     t0 = time.perf_counter()
     mem, mask = model.encode(**inp)
@@ -145,8 +151,9 @@ def cpu_reference_sample(sample_batch, sample_len, full_len, threads):
     t_enc, t_step = t1 - t0, (t2 - t1) / (sample_len - 1)
     full = t_enc + t_step * (full_len - 1)
     return {"images_per_s": sample_batch / full, "t_encode_s": t_enc, "t_step_s": t_step, "wall_s": t2 - t0,
-            "sample": (f"B={sample_batch} images, full-size random-init model, fp32, encode timed in full + "
-                       f"{sample_len - 1} greedy steps with KV cache; per-step time extrapolated to {full_len - 1} steps")}
+            "sample": (f"B={sample_batch} images of the batch-{BATCH} workload, full-size random-init model, fp32, "
+                       f"{threads} torch threads: encode timed in full + {sample_len - 1} greedy steps with KV cache; "
+                       f"per-step time extrapolated to {full_len - 1} steps")}
 
 
 def run_reference(args):
@@ -157,16 +164,17 @@ def run_reference(args):
     vals = []
     info = None
     for i in range(args.warmup + args.steps):
-        info = cpu_reference_sample(1, 17, MAX_LENGTH, threads)
+        info = cpu_reference_sample(4, 9, MAX_LENGTH, threads)
         if i >= args.warmup:
             vals.append(info["images_per_s"])
     v = statistics.mean(vals)
     out = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1000.0 / v if v else None, "higher_is_better": True,
+           "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / v if v else None, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"configs[1]: batch-{BATCH} synthetic 512x512, greedy <={MAX_LENGTH} tok, "
                                   "random-init MarkushGrapher-2 dims", "text_len": TEXT_LEN,
-                      "note": "CPU oracle (stock transformers UDOP+Swin restatement of the reference path) on host cores"},
+                      "note": "reference path = CPU oracle (stock transformers UDOP+Swin restatement; the reference's "
+                              "own model code lives in un-vendored forks and cannot be installed offline) on host cores"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": info["sample"]},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -299,13 +307,16 @@ def run_ours(args):
                        "decode_step_frac_of_hbm_peak": step_bytes / (step_ms * 1e-3) / 1e9 / peak},
             "roofline": {"kernel": "dec_attn_kernel<cross> (decoder cross-attention over the encoder memory)",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": 328.4e6 if (B == 32 and not args.small) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
+                                           "profiles/r1_ncu_crossattn.txt (batch 32, M = 1232)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": prof["bytes_per_launch"],
                          "ms_per_launch": prof["ms_per_launch"], "launches_timed": prof["launches"]},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            c = cpu_reference_sample(1, 17, args.max_length, threads)
+            c = cpu_reference_sample(4, 9, args.max_length, threads)
             out["cpu_baseline"] = {"value": c["images_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": c["sample"], "t_encode_s": c["t_encode_s"], "t_step_s": c["t_step_s"]}
         print(json.dumps(out))

@@ -634,10 +634,11 @@ void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes 
   p.num_kb = K / BK;
   const int tiles = (N + BM - 1) / BM;
   int ksplit = 1;
-  if (!store) ksplit = std::min(p.num_kb, std::max(1, 148 / tiles));
+  static const int target_ctas = getenv("MG_SKINNY_CTAS") ? atoi(getenv("MG_SKINNY_CTAS")) : 148;
+  if (!store) ksplit = std::min(p.num_kb, std::max(1, target_ctas / tiles));
   p.kb_per_cta = (p.num_kb + ksplit - 1) / ksplit;
   ksplit = (p.num_kb + p.kb_per_cta - 1) / p.kb_per_cta;
-  static const int max_stages = getenv("MG_SKINNY_STAGES") ? atoi(getenv("MG_SKINNY_STAGES")) : 2;
+  static const int max_stages = getenv("MG_SKINNY_STAGES") ? atoi(getenv("MG_SKINNY_STAGES")) : 4;
   p.stages = std::min(max_stages, p.kb_per_cta);  // <= 84 KB: CTAs of consecutive (PDL-overlapped) kernels co-reside
   p.pro = pro; p.lnw = lnw; p.eps = eps; p.scale = scale;
   p.zero_ptr = zero_ptr; p.zero_n = zero_n; p.store = store ? 1 : 0;

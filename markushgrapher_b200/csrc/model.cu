@@ -179,8 +179,11 @@ struct mg_model {
   float last_encode_ms = 0.f, last_decode_ms = 0.f;
   int64_t last_launches = 0;
   int* pinned_flag = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t own_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;  // second micro-batch lane of the greedy decode loop
+  cudaEvent_t lane_ev[3] = {nullptr, nullptr, nullptr};
+  int prof_bn = 0;
   // multi-GPU (image-batch sharding): one NCCL all-gather of the step's token ids per decode step
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
@@ -196,6 +199,9 @@ struct mg_model {
     scratch.release();
     if (pinned_flag) cudaFreeHost(pinned_flag);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
+    for (auto& e : lane_ev)
+      if (e) cudaEventDestroy(e);
     if (comm) nccl_api().CommDestroy(comm);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -792,11 +798,41 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   float* hbuf = a.get<float>((int64_t)B * c.d_ff);
   float* logits = a.get<float>((int64_t)B * Vld);
   int* finished = a.get<int>(B);
-  int* ctr = a.get<int>(8);  // [0]=step [1]=n_unfinished [2]=ticket [3]=global n_unfinished
+  int* gctr = a.get<int>(8);  // [3] = global n_unfinished (multi-GPU)
   const bool dist = comm != nullptr && dist_all_ids != nullptr && forced == nullptr;
   int* step_tok = a.get<int>(B);
   int* gathered = a.get<int>((int64_t)world * B);
   int* gfinished = a.get<int>((int64_t)world * B);
+
+  // ---- micro-batch lanes (experimental, MG_LANES=2; default 1).  The decode chain of one token is strictly
+  // sequential and alternates between latency-bound kernels (skinny linears) and the HBM-bound cross-attention
+  // stream; with two lanes the image batch is split in two and the same captured step runs on two streams so one
+  // lane can stream K/V while the other runs its linears.  Images are independent, so results are identical.
+  // Measured on B200 at batch 32: no gain (2.95 vs 2.93 ms/step) -- the half-batch kernels are as latency-bound
+  // as the full-batch ones and contend for shared memory -- so the default stays at one lane.
+  static const int env_lanes = getenv("MG_LANES") ? atoi(getenv("MG_LANES")) : 1;
+  const int nlanes = (B >= 8 && env_lanes >= 2) ? 2 : 1;
+  struct Lane {
+    int b0, bn;
+    cudaStream_t st;
+    int* ctr;  // [0]=step [1]=n_unfinished [2]=ticket
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+  };
+  Lane lanes[2];
+  if (nlanes == 2 && !aux_stream) {
+    MG_CHECK_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    MG_CHECK_CUDA(cudaEventCreateWithFlags(&lane_ev[0], cudaEventDisableTiming));
+    MG_CHECK_CUDA(cudaEventCreateWithFlags(&lane_ev[1], cudaEventDisableTiming));
+    MG_CHECK_CUDA(cudaEventCreateWithFlags(&lane_ev[2], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < nlanes; ++i) {
+    lanes[i].b0 = i == 0 ? 0 : (B + 1) / 2;
+    lanes[i].bn = nlanes == 1 ? B : (i == 0 ? (B + 1) / 2 : B - (B + 1) / 2);
+    lanes[i].st = i == 0 ? st : aux_stream;
+    lanes[i].ctr = a.get<int>(8);
+  }
+
   if (dist) {
     MG_CHECK_CUDA(cudaMemsetAsync(gfinished, 0, sizeof(int) * (size_t)world * B, st));
     MG_CHECK_CUDA(cudaMemsetAsync(dist_all_ids, 0, sizeof(int64_t) * (size_t)world * B * max_length, st));
@@ -805,114 +841,147 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     MG_CHECK_CUDA(cudaMemcpy2DAsync(dist_all_ids, sizeof(int64_t) * max_length, col0.data(), sizeof(int64_t),
                                     sizeof(int64_t), (size_t)world * B, cudaMemcpyHostToDevice, st));
     const int wb = world * B;
-    MG_CHECK_CUDA(cudaMemcpyAsync(ctr + 3, &wb, sizeof(int), cudaMemcpyHostToDevice, st));
+    MG_CHECK_CUDA(cudaMemcpyAsync(gctr + 3, &wb, sizeof(int), cudaMemcpyHostToDevice, st));
     MG_CHECK_CUDA(cudaStreamSynchronize(st));  // col0 / wb are host temporaries
   }
-  // exchange of one decode step: every rank learns every image's new token and applies the same stop rule
-  auto exchange = [&](int col) {
-    MG_CHECK_NCCL(nccl_api().AllGather(step_tok, gathered, (size_t)B, ncclInt32, comm, st));
-    launch_scatter_step(st, gathered, world * B, col, max_length, c.eos_token_id, dist_all_ids, gfinished, ctr + 3);
-    launches += 2;
-  };
   int64_t* ids_dev = out_ids;
-  launch_decode_init(st, shared, d, c.decoder_start_token_id, B, ids_dev, max_length, finished, ctr, ctr + 1, ctr + 2, x,
-                     forced, forced_ld);
-  ++launches;
+  for (int i = 0; i < nlanes; ++i) {
+    Lane& L = lanes[i];
+    launch_decode_init(st, shared, d, c.decoder_start_token_id, L.bn, ids_dev + (int64_t)L.b0 * max_length, max_length,
+                       finished + L.b0, L.ctr, L.ctr + 1, L.ctr + 2, x + (int64_t)L.b0 * d,
+                       forced ? forced + (int64_t)L.b0 * forced_ld : nullptr, forced_ld);
+    ++launches;
+  }
   // split-K accumulation buffers start at zero; afterwards each is re-zeroed by a later kernel of the chain
   MG_CHECK_CUDA(cudaMemsetAsync(qkv, 0, sizeof(float) * (size_t)B * 3 * d, st));
   MG_CHECK_CUDA(cudaMemsetAsync(q, 0, sizeof(float) * (size_t)B * d, st));
   MG_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * (size_t)B * c.d_ff, st));
+  if (nlanes == 2) {  // the second lane starts after the encoder, the K/V projection and the state reset
+    MG_CHECK_CUDA(cudaEventRecord(lane_ev[0], st));
+    MG_CHECK_CUDA(cudaStreamWaitEvent(aux_stream, lane_ev[0], 0));
+  }
 
-  // out[b0:b0+128] (+)= pro(x) W^T in slices of at most 128 rows
-  auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
-                 float scale, float* zp, int64_t zn, bool store) {
-    for (int b0 = 0; b0 < B; b0 += 128) {
-      const int bc = std::min(128, B - b0);
-      launch_skinny_tc(st, pro, xin + (int64_t)b0 * ldx, ldx, W.w, W.ldk, out + (int64_t)b0 * ld_out, ld_out, bc, W.N,
-                       W.K, lnw, c.ln_eps, scale, b0 == 0 ? zp : nullptr, zn, store);
-      ++launches;
-    }
-  };
-  auto one_step = [&]() {
+  // one decode step of one lane (rows [b0, b0+bn)) on the lane's stream
+  auto one_step = [&](Lane& Ln) {
+    cudaStream_t ls = Ln.st;
+    const int b0 = Ln.b0, bn = Ln.bn;
+    auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
+                   float scale, float* zp, int64_t zn, bool store) {
+      for (int r0 = 0; r0 < bn; r0 += 128) {
+        const int bc = std::min(128, bn - r0);
+        launch_skinny_tc(ls, pro, xin + (int64_t)(b0 + r0) * ldx, ldx, W.w, W.ldk, out + (int64_t)(b0 + r0) * ld_out,
+                         ld_out, bc, W.N, W.K, lnw, c.ln_eps, scale, r0 == 0 ? zp : nullptr, zn, store);
+        ++launches;
+      }
+    };
     for (int l = 0; l < NL; ++l) {
       DecLayer& L = dec[l];
       // self-attention block: RMSNorm fused into the QKV projection; zero duty: FF hidden buffer
-      lin(1, x, d, L.qkv, qkv, 3 * d, L.ln1, 1.f, hbuf, (int64_t)B * c.d_ff, false);
-      launch_dec_self_attn(st, qkv, B, H, d, skt[l], Tp, (int64_t)d * Tp, sv[l], d, (int64_t)Tp * d, ctr, Tp, dec_bias,
-                           lut_dec, ctx);
+      lin(1, x, d, L.qkv, qkv, 3 * d, L.ln1, 1.f, hbuf + (int64_t)b0 * c.d_ff, (int64_t)bn * c.d_ff, false);
+      launch_dec_self_attn(ls, qkv + (int64_t)b0 * 3 * d, bn, H, d, skt[l] + (int64_t)b0 * d * Tp, Tp, (int64_t)d * Tp,
+                           sv[l] + (int64_t)b0 * Tp * d, d, (int64_t)Tp * d, Ln.ctr, Tp, dec_bias, lut_dec,
+                           ctx + (int64_t)b0 * d);
       lin(0, ctx, d, L.o, x, d, nullptr, 1.f, nullptr, 0, false);  // x += o(ctx)
       // cross-attention block; zero duty: the QKV buffer just consumed by self-attention
-      lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv, (int64_t)B * 3 * d, false);
-      launch_cross_attn_stream(st, q, B, H, d, ckt[l], cv[l], Mp, mem_mask, ctx);
+      lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv + (int64_t)b0 * 3 * d, (int64_t)bn * 3 * d, false);
+      launch_cross_attn_stream(ls, q + (int64_t)b0 * d, bn, H, d, ckt[l] + (int64_t)b0 * d * Mp,
+                               cv[l] + (int64_t)b0 * Mp * d, Mp, mem_mask + (int64_t)b0 * Mp, ctx + (int64_t)b0 * d);
       lin(0, ctx, d, L.co, x, d, nullptr, 1.f, nullptr, 0, false);
       // feed-forward: RMSNorm fused into wi, ReLU fused into wo's operand load; zero duty: cross-attention q
-      lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q, (int64_t)B * d, false);
+      lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q + (int64_t)b0 * d, (int64_t)bn * d, false);
       lin(2, hbuf, c.d_ff, L.wo, x, d, nullptr, 1.f, nullptr, 0, false);
       launches += 2;
     }
     // final RMSNorm * d_model^-0.5 fused into the LM head (modeling_udop.py:1585-1590), direct store
     lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true);
-    launch_greedy_select(st, logits, B, V, Vld, shared, d, c.eos_token_id, c.pad_token_id, ids_dev, max_length,
-                         finished, ctr, ctr + 1, ctr + 2, x, step_logits, (int64_t)(max_length - 1) * V, V, forced,
-                         forced_ld, step_tok);
+    launch_greedy_select(ls, logits + (int64_t)b0 * Vld, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
+                         ids_dev + (int64_t)b0 * max_length, max_length, finished + b0, Ln.ctr, Ln.ctr + 1, Ln.ctr + 2,
+                         x + (int64_t)b0 * d,
+                         step_logits ? step_logits + (int64_t)b0 * (max_length - 1) * V : nullptr,
+                         (int64_t)(max_length - 1) * V, V, forced ? forced + (int64_t)b0 * forced_ld : nullptr,
+                         forced_ld, step_tok + b0);
     launches += 1;
+  };
+  // one step of every lane; in multi-GPU mode followed by the exchange of the step's token ids
+  auto exchange = [&](int col) {
+    if (nlanes == 2) {  // the all-gather reads both lanes' tokens ...
+      MG_CHECK_CUDA(cudaEventRecord(lane_ev[1], aux_stream));
+      MG_CHECK_CUDA(cudaStreamWaitEvent(st, lane_ev[1], 0));
+    }
+    MG_CHECK_NCCL(nccl_api().AllGather(step_tok, gathered, (size_t)B, ncclInt32, comm, st));
+    launch_scatter_step(st, gathered, world * B, col, max_length, c.eos_token_id, dist_all_ids, gfinished, gctr + 3);
+    launches += 2;
+    if (nlanes == 2) {  // ... and lane 1 must not overwrite them before it has run
+      MG_CHECK_CUDA(cudaEventRecord(lane_ev[2], st));
+      MG_CHECK_CUDA(cudaStreamWaitEvent(aux_stream, lane_ev[2], 0));
+    }
   };
 
   prof_ckt = ckt;
   prof_cv = cv;
   prof_q = q;
   prof_ctx = ctx;
+  prof_bn = lanes[0].bn;
   const int total_steps = max_length - 1;
   int done_steps = 0;
   // step 0 runs eagerly (lazy one-time initialisation happens outside graph capture) ...
-  one_step();
+  for (int i = 0; i < nlanes; ++i) one_step(lanes[i]);
   done_steps = 1;
   if (dist) exchange(1);
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
-  const int64_t per_step = launches;
   if (total_steps > 1) {
-    // ... then one step is captured and replayed; every kernel reads the step index from device memory
+    // ... then one step per lane is captured and replayed; every kernel reads the step index from device memory
     const int64_t before = launches;
-    MG_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    try {
-      one_step();
-    } catch (...) {
-      cudaGraph_t g2;
-      cudaStreamEndCapture(st, &g2);
-      throw;
+    for (int i = 0; i < nlanes; ++i) {
+      MG_CHECK_CUDA(cudaStreamBeginCapture(lanes[i].st, cudaStreamCaptureModeThreadLocal));
+      try {
+        one_step(lanes[i]);
+      } catch (...) {
+        cudaGraph_t g2;
+        cudaStreamEndCapture(lanes[i].st, &g2);
+        throw;
+      }
+      MG_CHECK_CUDA(cudaStreamEndCapture(lanes[i].st, &lanes[i].graph));
+      MG_CHECK_CUDA(cudaGraphInstantiate(&lanes[i].exec, lanes[i].graph, 0));
     }
-    MG_CHECK_CUDA(cudaStreamEndCapture(st, &graph));
-    MG_CHECK_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
-    if (getenv("MG_DUMP_GRAPH")) cudaGraphDebugDotPrint(graph, getenv("MG_DUMP_GRAPH"), 0);
+    if (getenv("MG_DUMP_GRAPH")) cudaGraphDebugDotPrint(lanes[0].graph, getenv("MG_DUMP_GRAPH"), 0);
     const int64_t step_launches = launches - before;
     launches = before;
-    pinned_flag[0] = dist ? world * B : B;
+    pinned_flag[0] = pinned_flag[1] = B;
     const int check_every = 16;
     bool stop = false;
     while (done_steps < total_steps && !stop) {
       const int n = std::min(check_every, total_steps - done_steps);
       for (int i = 0; i < n; ++i) {
-        MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+        for (int k = 0; k < nlanes; ++k) MG_CHECK_CUDA(cudaGraphLaunch(lanes[k].exec, lanes[k].st));
         if (dist) exchange(done_steps + i + 1);
       }
       launches += step_launches * n;
       done_steps += n;
-      // poll the "all finished" counter one window late so the GPU never drains
+      // poll the "all finished" counters one window late so the GPU never drains
       MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));
-      if (pinned_flag[0] == 0) stop = true;
-      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? ctr + 3 : ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (nlanes == 2) MG_CHECK_CUDA(cudaEventSynchronize(ev[5]));
+      if (dist ? pinned_flag[0] == 0 : (pinned_flag[0] + (nlanes == 2 ? pinned_flag[1] : 0)) == 0) stop = true;
+      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? gctr + 3 : lanes[0].ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
       MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
+      if (nlanes == 2) {
+        MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag + 1, lanes[1].ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, aux_stream));
+        MG_CHECK_CUDA(cudaEventRecord(ev[5], aux_stream));
+      }
     }
   }
-  (void)per_step;
+  if (nlanes == 2) {  // join the second lane back into the caller's stream
+    MG_CHECK_CUDA(cudaEventRecord(lane_ev[1], aux_stream));
+    MG_CHECK_CUDA(cudaStreamWaitEvent(st, lane_ev[1], 0));
+  }
   if (out_len) {
     launch_out_len(st, ids_dev, B, max_length, std::min(done_steps + 1, max_length), c.eos_token_id, out_len);
     ++launches;
   }
   MG_CHECK_CUDA(cudaStreamSynchronize(st));
-  if (gexec) cudaGraphExecDestroy(gexec);
-  if (graph) cudaGraphDestroy(graph);
+  for (int i = 0; i < nlanes; ++i) {
+    if (lanes[i].exec) cudaGraphExecDestroy(lanes[i].exec);
+    if (lanes[i].graph) cudaGraphDestroy(lanes[i].graph);
+  }
   if (steps_run) *steps_run = done_steps;
 }
 
@@ -1129,6 +1198,7 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
   m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
   MG_CHECK_CUDA(cudaEventRecord(m->ev[1], st));
   MG_CHECK_CUDA(cudaEventRecord(m->ev[3], st));
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[5], st));
   if (num_beams == 1)
     m->generate(st, B, max_length, out_ids, out_len, step_logits, steps_run);
   else
@@ -1194,6 +1264,7 @@ int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* i
   // position t of the (B, T, V) output; T steps == max_length T+1
   int64_t* ids_scratch = m->persist.get<int64_t>((int64_t)B * (T + 1));
   MG_CHECK_CUDA(cudaEventRecord(m->ev[3], st));
+  MG_CHECK_CUDA(cudaEventRecord(m->ev[5], st));
   m->generate(st, B, T + 1, ids_scratch, nullptr, logits, nullptr, decoder_input_ids, T);
   MG_API_END
 }
@@ -1261,7 +1332,9 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
     st = m->own_stream;
   }
   const mg_config& c = m->cfg;
-  const int B = m->cur_B, d = c.d_model, H = c.num_heads, Mp = m->cur_Mp, NL = (int)m->prof_ckt.size();
+  // the production launch shape: one micro-batch lane (prof_bn images) per launch
+  const int B = m->prof_bn > 0 ? m->prof_bn : m->cur_B;
+  const int d = c.d_model, H = c.num_heads, Mp = m->cur_Mp, NL = (int)m->prof_ckt.size();
   auto pass = [&]() {
     for (int l = 0; l < NL; ++l)
       launch_cross_attn_stream(st, m->prof_q, B, H, d, m->prof_ckt[l], m->prof_cv[l], Mp, m->mem_mask, m->prof_ctx);

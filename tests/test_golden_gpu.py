@@ -33,4 +33,9 @@ def test_cuda_matches_golden(name):
     assert np.array_equal(ids.cpu().numpy(), g["greedy_ids"])
     np.testing.assert_allclose(logits[:, 0].cpu().numpy(), g["step0_logits"], rtol=0, atol=5e-4)
     np.testing.assert_allclose(logits[:, -1].cpu().numpy(), g["last_logits"], rtol=0, atol=5e-4)
+    beam = eng.generate(**inp, max_length=max_len, num_beams=4)
+    assert np.array_equal(beam.cpu().numpy(), g["beam4_ids"])
+    tf = eng.forward_logits(inp["input_ids"], inp["bbox"], inp["pixel_values"],
+                            torch.from_numpy(g["greedy_ids"][:, :-1]), inp["attention_mask"])
+    np.testing.assert_allclose(tf[:, -1].cpu().numpy(), g["tf_last_logits"], rtol=0, atol=5e-4)
     eng.close()
