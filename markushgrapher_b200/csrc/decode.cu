@@ -372,7 +372,9 @@ void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out) {
 // Greedy selection (GenerationMixin._sample :2762-2805): first-max argmax over fp32 logits, finished rows
 // emit pad, EOS bookkeeping, token append, next-step input embedding.  One CTA per image.  The last CTA to
 // finish advances the device step counter and publishes the "all rows finished" flag.
-__global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ logits, int V, int64_t ld,
+__global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ part_val,
+                                                            const int* __restrict__ part_idx, int n_part,
+                                                            const float* __restrict__ logits, int V, int64_t ld,
                                                             const float* __restrict__ emb, int D, int eos, int pad,
                                                             int64_t* __restrict__ out_ids, int out_ld,
                                                             int* __restrict__ finished, int* __restrict__ step_ptr,
@@ -388,12 +390,26 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
   const int step = *step_ptr;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float x = lg[i];
-    if (logits_dump) logits_dump[(int64_t)b * dump_bs + (int64_t)step * dump_ss + i] = x;
-    if (x > best || (x == best && i < bi)) {
-      best = x;
-      bi = i;
+  if (part_val) {  // per-tile maxima were produced by the LM-head epilogue: reduce n_part candidates
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+      const float x = part_val[(int64_t)b * n_part + i];
+      const int xi = part_idx[(int64_t)b * n_part + i];
+      if (x > best || (x == best && xi < bi)) {
+        best = x;
+        bi = xi;
+      }
+    }
+    if (logits_dump)
+      for (int i = threadIdx.x; i < V; i += blockDim.x)
+        logits_dump[(int64_t)b * dump_bs + (int64_t)step * dump_ss + i] = lg[i];
+  } else {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      const float x = lg[i];
+      if (logits_dump) logits_dump[(int64_t)b * dump_bs + (int64_t)step * dump_ss + i] = x;
+      if (x > best || (x == best && i < bi)) {
+        best = x;
+        bi = i;
+      }
     }
   }
 #pragma unroll
@@ -448,11 +464,13 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
   }
 }
 
-void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
+void launch_greedy_select(cudaStream_t st, const float* part_val, const int* part_idx, int n_part, const float* logits,
+                          int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
                           int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok) {
-  launch_pdl(greedy_select_kernel, dim3(B), dim3(256), (size_t)0, st, logits, V, ld, emb, D, eos, pad, out_ids, out_ld,
+  launch_pdl(greedy_select_kernel, dim3(B), dim3(256), (size_t)0, st, part_val, part_idx, n_part, logits, V, ld, emb, D,
+             eos, pad, out_ids, out_ld,
              finished, step_ptr, n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss, forced, forced_ld,
              step_tok);
 }

@@ -392,6 +392,10 @@ struct alignas(64) SkinnyParams {
   float* zero_ptr;
   long long zero_n;
   int store;
+  // optional fused partial argmax over this CTA's 128 features, per activation row (LM head -> greedy selection):
+  // amax_val/amax_idx [B][gridDim.x]; ties resolve to the lowest feature index (torch.argmax semantics)
+  float* amax_val;
+  int* amax_idx;
 };
 
 template <int NG>
@@ -598,6 +602,39 @@ __global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant
           }
         }
       }
+      if (p.amax_val) {  // warp-level (value, index) max per activation row, then across the 4 epilogue warps
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float bv = (n < p.N) ? __uint_as_float(rr[j]) * s_rs[min(c0 + j, R - 1)] : -INFINITY;
+          int bi = n;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          if (lane == 0) {
+            s_part[(c0 + j) * 4 + q] = bv;                              // s_part is free after the statistics
+            reinterpret_cast<int*>(s_rs + R * 5)[(c0 + j) * 4 + q] = bi;  // [R][4] ints after s_part
+          }
+        }
+      }
+    }
+    if (p.amax_val) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t < p.B) {
+        const int* s_pi = reinterpret_cast<const int*>(s_rs + R * 5);
+        float bv = s_part[t * 4];
+        int bi = s_pi[t * 4];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float ov = s_part[t * 4 + w];
+          const int oi = s_pi[t * 4 + w];
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        p.amax_val[(int64_t)t * gridDim.x + blockIdx.x] = bv;
+        p.amax_idx[(int64_t)t * gridDim.x + blockIdx.x] = bi;
+      }
     }
   }
   tc_fence_before();
@@ -608,7 +645,7 @@ __global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant
 template <int NG>
 static void launch_skinny_ng(cudaStream_t st, const SkinnyParams& p, dim3 grid) {
   constexpr int STAGE = 2 * A_BYTES + 2 * (32 * NG * BK * 2);
-  const int smem = p.stages * STAGE + 1024 + 256 + 32 * NG * 5 * 4 + 64;
+  const int smem = p.stages * STAGE + 1024 + 256 + 32 * NG * 9 * 4 + 64;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     MG_CHECK_CUDA(cudaFuncSetAttribute(skinny_tc_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -619,7 +656,8 @@ static void launch_skinny_ng(cudaStream_t st, const SkinnyParams& p, dim3 grid) 
 
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
-                      bool store) {
+                      bool store, float* amax_val, int* amax_idx) {
+  MG_REQUIRE(amax_val == nullptr || (store && amax_idx != nullptr), "fused argmax needs the direct-store (no split-K) mode");
   MG_REQUIRE(K % BK == 0 && ldx % 4 == 0, "skinny linear: K must be a multiple of 64");
   MG_REQUIRE(pro != 1 || K <= 1024, "skinny linear: fused RMSNorm needs K <= 1024");
   MG_REQUIRE(B >= 1 && B <= 128, "skinny linear: 1 <= B <= 128 per launch");
@@ -642,6 +680,7 @@ void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes 
   p.stages = std::min(max_stages, p.kb_per_cta);  // <= 84 KB: CTAs of consecutive (PDL-overlapped) kernels co-reside
   p.pro = pro; p.lnw = lnw; p.eps = eps; p.scale = scale;
   p.zero_ptr = zero_ptr; p.zero_n = zero_n; p.store = store ? 1 : 0;
+  p.amax_val = amax_val; p.amax_idx = amax_idx;
   dim3 grid(tiles, ksplit);
   if (B <= 32) launch_skinny_ng<1>(st, p, grid);
   else if (B <= 64) launch_skinny_ng<2>(st, p, grid);

@@ -41,7 +41,8 @@ void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D,
 void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, const float* v,
                               int Mp, const int* mask, float* ctx);
 void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
-void launch_greedy_select(cudaStream_t st, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
+// part_val/part_idx: optional [B][n_part] partial maxima from the LM-head epilogue (then `logits` is only dumped)
+void launch_greedy_select(cudaStream_t st, const float* part_val, const int* part_idx, int n_part, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
                           int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok);
@@ -82,6 +83,6 @@ void launch_beam_finalize(cudaStream_t st, const BeamState& s, int pad, int64_t*
 // gemm_tc.cu: tensor-core skinny linear with fused prologue (pro: 0 none, 1 RMSNorm, 2 ReLU), split-K atomics
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
-                      bool store);
+                      bool store, float* amax_val = nullptr, int* amax_idx = nullptr);
 
 }  // namespace mg

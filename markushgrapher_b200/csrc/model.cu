@@ -797,6 +797,9 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   float* ctx = a.get<float>((int64_t)B * d);
   float* hbuf = a.get<float>((int64_t)B * c.d_ff);
   float* logits = a.get<float>((int64_t)B * Vld);
+  const int n_part = (V + 127) / 128;  // LM-head tiles: per-tile (max, argmax) from the GEMM epilogue
+  float* part_val = a.get<float>((int64_t)B * n_part);
+  int* part_idx = a.get<int>((int64_t)B * n_part);
   int* finished = a.get<int>(B);
   int* gctr = a.get<int>(8);  // [3] = global n_unfinished (multi-GPU)
   const bool dist = comm != nullptr && dist_all_ids != nullptr && forced == nullptr;
@@ -866,11 +869,13 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     cudaStream_t ls = Ln.st;
     const int b0 = Ln.b0, bn = Ln.bn;
     auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
-                   float scale, float* zp, int64_t zn, bool store) {
+                   float scale, float* zp, int64_t zn, bool store, bool amax = false) {
       for (int r0 = 0; r0 < bn; r0 += 128) {
         const int bc = std::min(128, bn - r0);
         launch_skinny_tc(ls, pro, xin + (int64_t)(b0 + r0) * ldx, ldx, W.w, W.ldk, out + (int64_t)(b0 + r0) * ld_out,
-                         ld_out, bc, W.N, W.K, lnw, c.ln_eps, scale, r0 == 0 ? zp : nullptr, zn, store);
+                         ld_out, bc, W.N, W.K, lnw, c.ln_eps, scale, r0 == 0 ? zp : nullptr, zn, store,
+                         amax ? part_val + (int64_t)(b0 + r0) * n_part : nullptr,
+                         amax ? part_idx + (int64_t)(b0 + r0) * n_part : nullptr);
         ++launches;
       }
     };
@@ -893,8 +898,9 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       launches += 2;
     }
     // final RMSNorm * d_model^-0.5 fused into the LM head (modeling_udop.py:1585-1590), direct store
-    lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true);
-    launch_greedy_select(ls, logits + (int64_t)b0 * Vld, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
+    lin(1, x, d, lm_head, logits, (int)Vld, dec_final_ln, c.logit_scale, nullptr, 0, true, true);
+    launch_greedy_select(ls, part_val + (int64_t)b0 * n_part, part_idx + (int64_t)b0 * n_part, n_part,
+                         logits + (int64_t)b0 * Vld, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
                          ids_dev + (int64_t)b0 * max_length, max_length, finished + b0, Ln.ctr, Ln.ctr + 1, Ln.ctr + 2,
                          x + (int64_t)b0 * d,
                          step_logits ? step_logits + (int64_t)b0 * (max_length - 1) * V : nullptr,
