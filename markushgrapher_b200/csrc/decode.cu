@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
                                                        int64_t v_ld, int64_t v_bs, const int* __restrict__ step_ptr,
                                                        int n_keys_cross, const int* __restrict__ mask, int mask_ld,
                                                        const float* __restrict__ dec_bias, const int* __restrict__ lut,
-                                                       int H, int D, float* __restrict__ ctx) {
+                                                       int H, int D, float* __restrict__ ctx, int kpad_keys) {
   constexpr int HD = 64;
   extern __shared__ __align__(16) float sm[];
   float* sq = sm;             // [64]
@@ -56,36 +56,48 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
     }
   }
   __syncthreads();
-  // ---- scores over cached keys: thread = 4 consecutive keys, loop over d (coalesced float4 rows of K^T)
+  // ---- scores over cached keys.  Work item = (group of 4 consecutive keys, quarter of the 64 d-rows): at a few
+  // hundred cached keys this keeps all 256 threads busy with ONE batch of 16 independent float4 loads each
+  // (coalesced rows of K^T) instead of a quarter of the threads running four dependent batches.  The four partial
+  // sums of a key are combined in the bias pass below.
   const int n4 = ncache >> 2;
-  for (int g = tid; g < n4; g += 256) {
+  float* scp = sc + ((kpad_keys + 3) & ~3);  // [3][kpad] partials of d-quarters 1..3 (quarter 0 lives in sc)
+  for (int u = tid; u < n4 * 4; u += 256) {
+    const int dq = u / n4, g = u - dq * n4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* col = reinterpret_cast<const float4*>(ktb) + g;
+    const float4* col = reinterpret_cast<const float4*>(ktb + (int64_t)(dq * 16) * kt_ld) + g;
     const int64_t ld4 = kt_ld >> 2;
-#pragma unroll 16
-    for (int d = 0; d < HD; ++d) {
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
       const float4 kk = __ldg(col + d * ld4);
-      const float qd = sq[d];
+      const float qd = sq[dq * 16 + d];
       a.x += qd * kk.x; a.y += qd * kk.y; a.z += qd * kk.z; a.w += qd * kk.w;
     }
-    reinterpret_cast<float4*>(sc)[g] = a;
+    float* dst = dq == 0 ? sc : scp + (int64_t)(dq - 1) * kpad_keys;
+    reinterpret_cast<float4*>(dst)[g] = a;
   }
-  for (int j = (n4 << 2) + tid; j < ncache; j += 256) {  // ragged tail (self only: ncache = step)
+  for (int j = (n4 << 2) + tid; j < ncache; j += 256) {  // ragged tail (< 4 keys)
     float a = 0.f;
 #pragma unroll 16
     for (int d = 0; d < HD; ++d) a += sq[d] * ktb[(int64_t)d * kt_ld + j];
     sc[j] = a;
+    scp[j] = 0.f;
+    scp[kpad_keys + j] = 0.f;
+    scp[2 * kpad_keys + j] = 0.f;
   }
   if (SELF && tid == 0) {
     float a = 0.f;
     for (int d = 0; d < HD; ++d) a += sred[d];
     sc[step] = a;
+    scp[step] = 0.f;
+    scp[kpad_keys + step] = 0.f;
+    scp[2 * kpad_keys + step] = 0.f;
   }
   __syncthreads();
   // ---- bias / mask, max
   float mx = -INFINITY;
   for (int j = tid; j < nk; j += 256) {
-    float s = sc[j];
+    float s = (sc[j] + scp[j]) + (scp[kpad_keys + j] + scp[2 * kpad_keys + j]);
     if (SELF) {
       s += dec_bias[lut[step - j] * H + h];  // causal mask is all-visible for the newest token
     } else {
@@ -127,7 +139,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* v4 = reinterpret_cast<const float4*>(vb) + c;
   const int64_t vld4 = v_ld >> 2;
-#pragma unroll 4
+#pragma unroll 16
   for (int j = r; j < ncache; j += 16) {
     const float4 vv = __ldg(v4 + (int64_t)j * vld4);
     const float p = sc[j];
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(256) dec_attn_kernel(const float* __restrict__
   }
 }
 
-static size_t dec_attn_smem(int max_keys) { return (size_t)(64 + 64 + 16 * 64 + ((max_keys + 3) / 4) * 4) * sizeof(float); }
+static size_t dec_attn_smem(int max_keys) { return (size_t)(64 + 64 + 16 * 64 + 4 * (((max_keys + 3) / 4) * 4)) * sizeof(float); }
 
 void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D, float* kt, int64_t kt_ld,
                           int64_t kt_bs, float* v, int64_t v_ld, int64_t v_bs, const int* step_ptr, int max_keys,
@@ -156,7 +168,7 @@ void launch_dec_self_attn(cudaStream_t st, const float* qkv, int B, int H, int D
   MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
   dim3 grid(H, B);
   launch_pdl(dec_attn_kernel<true>, grid, dim3(256), dec_attn_smem(max_keys), st, qkv, 3 * D, kt, kt_ld, kt_bs, v, v_ld,
-             v_bs, step_ptr, 0, (const int*)nullptr, 0, dec_bias, lut, H, D, ctx);
+             v_bs, step_ptr, 0, (const int*)nullptr, 0, dec_bias, lut, H, D, ctx, ((max_keys + 3) / 4) * 4);
 }
 
 void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, int64_t kt_ld,
@@ -167,7 +179,8 @@ void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D,
   dim3 grid(H, B);
   dec_attn_kernel<false><<<grid, 256, dec_attn_smem(n_keys), st>>>(q, D, const_cast<float*>(kt), kt_ld, kt_bs,
                                                                    const_cast<float*>(v), v_ld, v_bs, nullptr, n_keys,
-                                                                   mask, mask_ld, nullptr, nullptr, H, D, ctx);
+                                                                   mask, mask_ld, nullptr, nullptr, H, D, ctx,
+                                                                   ((n_keys + 3) / 4) * 4);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 
