@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmg_b200.so")
+LIB_PATH = os.environ.get("MG_B200_LIB", os.path.join(_HERE, "lib", "libmg_b200.so"))  # override: instrumented builds
 
 _lib = None
 
