@@ -399,7 +399,7 @@ struct alignas(64) SkinnyParams {
 };
 
 template <int NG>
-__global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant__ SkinnyParams p) {
+__global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant__ SkinnyParams p) {
   constexpr int R = 32 * NG;             // activation rows = UMMA N
   constexpr int X_BYTES = R * BK * 2;    // one plane of the activation tile
   constexpr int STAGE = 2 * A_BYTES + 2 * X_BYTES;
@@ -480,6 +480,44 @@ __global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant
       }
       umma_commit(tmem_full_bar);
     }
+  } else if (warp >= 6) {
+    // ---------------------------------------------------------------- statistic warps (6..9, 128 threads)
+    // RMSNorm row statistic over the FULL row, computed concurrently with the activation staging of the worker
+    // warps (it used to follow it: +2.2 us on the critical path of every RMSNorm-fused linear)
+    const int t = threadIdx.x - 192;
+    const int wq = warp - 6;  // 0..3
+    griddep_wait();
+    if (p.pro == 1) {
+      // K <= 1024 here (d_model): each thread owns at most two float4 of a row; loads are unconditional
+      // (rows / columns out of range are clamped and weighted by 0) so 16 of them are in flight per batch
+      const int n4row = p.K >> 2;
+      const int ca = min(t, n4row - 1), cb = min(t + 128, n4row - 1);
+      const float wa = t < n4row ? 1.f : 0.f, wb = (t + 128) < n4row ? 1.f : 0.f;
+      for (int r0 = 0; r0 < R; r0 += 8) {
+        float4 qa[8], qb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)min(r0 + j, p.B - 1) * p.ldx);
+          qa[j] = xr[ca];
+          qb[j] = xr[cb];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float ss = wa * (qa[j].x * qa[j].x + qa[j].y * qa[j].y + qa[j].z * qa[j].z + qa[j].w * qa[j].w) +
+                     wb * (qb[j].x * qb[j].x + qb[j].y * qb[j].y + qb[j].z * qb[j].z + qb[j].w * qb[j].w);
+          ss = warp_sum(ss);
+          if (lane == 0) s_part[(r0 + j) * 4 + wq] = ss;
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (t < R) {
+        const float ss = (s_part[t * 4] + s_part[t * 4 + 1]) + (s_part[t * 4 + 2] + s_part[t * 4 + 3]);
+        s_rs[t] = rsqrtf(ss / (float)p.K + p.eps) * p.scale;
+      }
+    } else {
+      if (t < R) s_rs[t] = p.scale;
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");
   } else {
     // ---------------------------------------------------------------- workers (warps 2..5, 128 threads)
     const int t = threadIdx.x - 64;
@@ -547,39 +585,7 @@ __global__ void __launch_bounds__(192, 1) skinny_tc_kernel(const __grid_constant
       for (int64_t i = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + t; i < n4; i += nthreads)
         z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // RMSNorm row statistic over the FULL row (while TMA / MMA are in flight)
-    const int wq = warp - 2;  // 0..3
-    if (p.pro == 1) {
-      // K <= 1024 here (d_model): each thread owns at most two float4 of a row; loads are unconditional
-      // (rows / columns out of range are clamped and weighted by 0) so 16 of them are in flight per batch
-      const int n4row = p.K >> 2;
-      const int ca = min(t, n4row - 1), cb = min(t + 128, n4row - 1);
-      const float wa = t < n4row ? 1.f : 0.f, wb = (t + 128) < n4row ? 1.f : 0.f;
-      for (int r0 = 0; r0 < R; r0 += 8) {
-        float4 qa[8], qb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)min(r0 + j, p.B - 1) * p.ldx);
-          qa[j] = xr[ca];
-          qb[j] = xr[cb];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float ss = wa * (qa[j].x * qa[j].x + qa[j].y * qa[j].y + qa[j].z * qa[j].z + qa[j].w * qa[j].w) +
-                     wb * (qb[j].x * qb[j].x + qb[j].y * qb[j].y + qb[j].z * qb[j].z + qb[j].w * qb[j].w);
-          ss = warp_sum(ss);
-          if (lane == 0) s_part[(r0 + j) * 4 + wq] = ss;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (t < R) {
-        const float ss = (s_part[t * 4] + s_part[t * 4 + 1]) + (s_part[t * 4 + 2] + s_part[t * 4 + 3]);
-        s_rs[t] = rsqrtf(ss / (float)p.K + p.eps) * p.scale;
-      }
-    } else {
-      if (t < R) s_rs[t] = p.scale;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 3, 256;" ::: "memory");  // row scales s_rs[] published by the statistic warps
     // ---------------------------------------------------------------- epilogue
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -651,7 +657,7 @@ static void launch_skinny_ng(cudaStream_t st, const SkinnyParams& p, dim3 grid) 
     MG_CHECK_CUDA(cudaFuncSetAttribute(skinny_tc_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_smem = 200 * 1024;
   }
-  launch_pdl(skinny_tc_kernel<NG>, grid, dim3(192), (size_t)smem, st, p);
+  launch_pdl(skinny_tc_kernel<NG>, grid, dim3(320), (size_t)smem, st, p);
 }
 
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
