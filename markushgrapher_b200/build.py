@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = ["gemm_tc.cu", "ops.cu", "swin.cu", "decode.cu", "beam.cu", "model.cu", "api_ops.cu"]
+SRC = ["gemm_tc.cu", "ops.cu", "swin.cu", "decode.cu", "decode_mega.cu", "beam.cu", "model.cu", "api_ops.cu"]
 OUT = os.path.join(HERE, "lib", "libmg_b200.so")
 
 
@@ -21,6 +21,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     common = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + csrc]
+    common += os.environ.get("MG_B200_CFLAGS", "").split()  # e.g. -DMK_FINE for the in-kernel phase profile
     procs = []
     objs = []
     for s in srcs:

@@ -85,4 +85,46 @@ void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes 
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
                       bool store, float* amax_val = nullptr, int* amax_idx = nullptr);
 
+// ---- decode_mega.cu: the fused persistent decode step (one cooperative kernel per generated token)
+struct MegaLin {           // a linear layer as a stream of pre-swizzled 32 KB (tile, k-block) weight tiles
+  const uint8_t* w = nullptr;  // [tiles][num_kb][hi 16 KB | lo 16 KB]
+  int N = 0, K = 0;
+  int tiles = 0, num_kb = 0;
+  int kb_per_item = 0, ksplit = 0;  // work items = tiles * ksplit, item -> (tile = it / ksplit, k-slice = it % ksplit)
+};
+struct MegaLayer {
+  MegaLin lin[6];      // qkv, o, cq, co, wi, wo
+  const float* ln[3];  // RMSNorm weights before qkv / cq / wi
+  float* skb;        // self K cache [B][H][Tp/32][64][32]
+  float* svb;        // self V cache [B][H][Tp][64]
+  const float* ckt;  // cross K^T [B][H][64][Mp]
+  const float* cv;   // cross V   [B][H][Mp][64]
+};
+struct MegaParams {
+  const MegaLayer* layers;  // device array [NL]
+  int NL;
+  MegaLin lm_head;
+  const float* final_ln;
+  float logit_scale, eps;
+  int B, H, D, DFF, Mp, Tp;
+  float *x, *qkv, *q, *ctx, *hbuf, *logits;
+  int ld_logits;
+  float* part_val;
+  int* part_idx;
+  const int* step_ptr;
+  const int* mem_mask;
+  const float* dec_bias;
+  const int* lut;
+  unsigned* bar_ctr;  // [2], zero before the first step
+  int gate = 1;          // 1: attention K/V streams wait until the consumers enter their phase
+  int dbg = 0;           // profiling builds (-DMK_FINE) only: 1 = skip the reductions, 2 = skip the TMEM loads
+  int max_inflight = 5;  // bulk loads one SM keeps in flight (<= ring stages)
+  unsigned long long* prof = nullptr;  // debug: [CTAs][256][2] globaltimer at (work done, barrier passed) per phase
+};
+size_t mega_lin_bytes(int N, int K);
+// tiles the planes of one linear into dst (mega_lin_bytes(N, K) bytes) and fills the work split for n_ctas CTAs
+MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst);
+int mega_max_ctas();  // CTAs of the cooperative launch (= SM count), 0 if the device cannot run it
+void launch_decode_step(cudaStream_t st, const MegaParams& p, int n_ctas);
+
 }  // namespace mg

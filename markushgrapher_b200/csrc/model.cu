@@ -192,6 +192,12 @@ struct mg_model {
   std::vector<float*> prof_ckt, prof_cv;
   float* prof_q = nullptr;
   float* prof_ctx = nullptr;
+  // fused persistent decode step (decode_mega.cu): pre-swizzled weight tiles + per-layer table
+  int mega_ctas = 0;
+  std::vector<MegaLayer> mega_layers;  // weight fields filled at finalize, cache pointers per generate call
+  MegaLin mega_lm;
+  MegaLayer* mega_layers_dev = nullptr;
+  unsigned* mega_bar = nullptr;
 
   ~mg_model() {
     for (void* p : owned) cudaFree(p);
@@ -441,6 +447,35 @@ void mg_model::finalize(cudaStream_t st) {
     for (int i = 0; i < 4096; ++i) ldx[i] = ld[std::min<int>(i, c.rel_max_distance)];
     lut_dec = upload_lut(st, ldx);
     lut_dec_n = 4096;
+  }
+  // ---- fused decode step: decoder weights re-tiled as a stream of pre-swizzled 32 KB shared-memory images
+  {
+    const char* mode = getenv("MG_DECODE");
+    const bool want = mode && std::string(mode) == "mega";  // opt-in until it beats the kernel chain
+    mega_ctas = (want && split2) ? mega_max_ctas() : 0;
+    if (mega_ctas > 0) {
+      const int NL = c.num_decoder_layers, dff = c.d_ff;
+      size_t per_layer = mega_lin_bytes(3 * d, d) + 3 * mega_lin_bytes(d, d) + mega_lin_bytes(dff, d) + mega_lin_bytes(d, dff);
+      uint8_t* buf = own<uint8_t>((int64_t)(per_layer * NL + mega_lin_bytes(V, d)));
+      mega_layers.resize(NL);
+      auto tile = [&](const LinearW& W, bool store) {
+        MegaLin L = make_mega_lin(st, W.w, W.N, W.K, W.ldk, store, mega_ctas, buf);
+        buf += mega_lin_bytes(W.N, W.K);
+        return L;
+      };
+      for (int i = 0; i < NL; ++i) {
+        MegaLayer& M = mega_layers[i];
+        const DecLayer& L = dec[i];
+        M.lin[0] = tile(L.qkv, false); M.lin[1] = tile(L.o, false); M.lin[2] = tile(L.cq, false);
+        M.lin[3] = tile(L.co, false); M.lin[4] = tile(L.wi, false); M.lin[5] = tile(L.wo, false);
+        M.ln[0] = L.ln1; M.ln[1] = L.ln2; M.ln[2] = L.ln3;
+        M.skb = M.svb = nullptr; M.ckt = M.cv = nullptr;
+      }
+      mega_lm = tile(lm_head, true);
+      mega_layers_dev = own<MegaLayer>(NL);
+      mega_bar = own<unsigned>(4);
+      MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, 4 * sizeof(unsigned), st));
+    }
   }
   MG_CHECK_CUDA(cudaMallocHost((void**)&pinned_flag, 64));
   for (auto& e : ev) MG_CHECK_CUDA(cudaEventCreate(&e));
@@ -780,7 +815,9 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
   Arena& a = scratch;
   a.reset();
-  const int Tp = (int)rup(max_length, 4);
+  // fused persistent decode step (decode_mega.cu) whenever the batch fits one activation tile
+  const bool use_mega = mega_ctas > 0 && B <= 32 && max_length <= 1024 && Mp <= 2048;
+  const int Tp = (int)rup(max_length, use_mega ? 32 : 4);
   const int64_t Vld = rup(V, 4);
 
   std::vector<float*> ckt(NL), cv(NL);
@@ -814,7 +851,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   // Measured on B200 at batch 32: no gain (2.95 vs 2.93 ms/step) -- the half-batch kernels are as latency-bound
   // as the full-batch ones and contend for shared memory -- so the default stays at one lane.
   static const int env_lanes = getenv("MG_LANES") ? atoi(getenv("MG_LANES")) : 1;
-  const int nlanes = (B >= 8 && env_lanes >= 2) ? 2 : 1;
+  const int nlanes = (B >= 8 && env_lanes >= 2 && !use_mega) ? 2 : 1;
   struct Lane {
     int b0, bn;
     cudaStream_t st;
@@ -865,9 +902,42 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   }
 
   // one decode step of one lane (rows [b0, b0+bn)) on the lane's stream
+  MegaParams mp;
+  if (use_mega) {
+    for (int l = 0; l < NL; ++l) {
+      mega_layers[l].skb = skt[l];
+      mega_layers[l].svb = sv[l];
+      mega_layers[l].ckt = ckt[l];
+      mega_layers[l].cv = cv[l];
+    }
+    MG_CHECK_CUDA(cudaMemcpyAsync(mega_layers_dev, mega_layers.data(), sizeof(MegaLayer) * NL, cudaMemcpyHostToDevice, st));
+    MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, 4 * sizeof(unsigned), st));
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));  // pageable source
+    mp.layers = mega_layers_dev; mp.NL = NL; mp.lm_head = mega_lm; mp.final_ln = dec_final_ln;
+    mp.logit_scale = c.logit_scale; mp.eps = c.ln_eps;
+    mp.B = B; mp.H = H; mp.D = d; mp.DFF = c.d_ff; mp.Mp = Mp; mp.Tp = Tp;
+    mp.x = x; mp.qkv = qkv; mp.q = q; mp.ctx = ctx; mp.hbuf = hbuf; mp.logits = logits; mp.ld_logits = (int)Vld;
+    mp.part_val = part_val; mp.part_idx = part_idx; mp.step_ptr = lanes[0].ctr; mp.mem_mask = mem_mask;
+    mp.dec_bias = dec_bias; mp.lut = lut_dec; mp.bar_ctr = mega_bar;
+    if (getenv("MG_MEGA_DBG")) mp.dbg = atoi(getenv("MG_MEGA_DBG"));
+    if (getenv("MG_MEGA_GATE")) mp.gate = atoi(getenv("MG_MEGA_GATE"));
+    if (getenv("MG_MEGA_INFLIGHT")) mp.max_inflight = std::max(1, std::min(5, atoi(getenv("MG_MEGA_INFLIGHT"))));
+    if (getenv("MG_MEGA_PROF")) {  // debug: per-phase timestamps of the last step, dumped after the loop
+      mp.prof = a.get<unsigned long long>((int64_t)mega_ctas * 1024);
+      MG_CHECK_CUDA(cudaMemsetAsync(mp.prof, 0, sizeof(unsigned long long) * (size_t)mega_ctas * 1024, st));
+    }
+  }
   auto one_step = [&](Lane& Ln) {
     cudaStream_t ls = Ln.st;
     const int b0 = Ln.b0, bn = Ln.bn;
+    if (use_mega) {
+      launch_decode_step(ls, mp, mega_ctas);
+      launch_greedy_select(ls, part_val, part_idx, n_part, logits, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
+                           ids_dev, max_length, finished, Ln.ctr, Ln.ctr + 1, Ln.ctr + 2, x,
+                           step_logits, (int64_t)(max_length - 1) * V, V, forced, forced_ld, step_tok);
+      launches += 2;
+      return;
+    }
     auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
                    float scale, float* zp, int64_t zn, bool store, bool amax = false) {
       for (int r0 = 0; r0 < bn; r0 += 128) {
@@ -934,7 +1004,23 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   for (int i = 0; i < nlanes; ++i) one_step(lanes[i]);
   done_steps = 1;
   if (dist) exchange(1);
-  if (total_steps > 1) {
+  if (total_steps > 1 && use_mega) {
+    // two launches per token: nothing to capture, the host simply runs ahead of the GPU
+    pinned_flag[0] = pinned_flag[1] = B;
+    bool stop = false;
+    while (done_steps < total_steps && !stop) {
+      const int n = std::min(16, total_steps - done_steps);
+      for (int i = 0; i < n; ++i) {
+        one_step(lanes[0]);
+        if (dist) exchange(done_steps + i + 1);
+      }
+      done_steps += n;
+      MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));  // poll the "all finished" counter one window late
+      if (pinned_flag[0] == 0) stop = true;
+      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? gctr + 3 : lanes[0].ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
+    }
+  } else if (total_steps > 1) {
     // ... then one step per lane is captured and replayed; every kernel reads the step index from device memory
     const int64_t before = launches;
     for (int i = 0; i < nlanes; ++i) {
@@ -984,6 +1070,14 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     ++launches;
   }
   MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (use_mega && mp.prof) {
+    std::vector<unsigned long long> h((size_t)mega_ctas * 1024);
+    MG_CHECK_CUDA(cudaMemcpy(h.data(), mp.prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("MG_MEGA_PROF"), "wb")) {
+      fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+      fclose(f);
+    }
+  }
   for (int i = 0; i < nlanes; ++i) {
     if (lanes[i].exec) cudaGraphExecDestroy(lanes[i].exec);
     if (lanes[i].graph) cudaGraphDestroy(lanes[i].graph);
