@@ -365,6 +365,233 @@ void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int
 }
 
 // =====================================================================================================
+// "kv24" cross K/V: the decode loop re-reads the image's cross K and V of every layer once per generated token,
+// which is the bulk of the step's HBM traffic.  Both are stored with 24 significant bits per element -- fp32
+// rounded to nearest-even at mantissa bit 15, i.e. the same 2^-17 relative precision as the split-bf16 GEMM operands
+// that produced them -- as a 16-bit plane (sign, exponent, 7 mantissa bits = the bf16 truncation) plus an 8-bit
+// plane (the next 8 mantissa bits).  3 bytes instead of 4: the dominant kernel moves 25 % fewer bytes.
+// Per (image, head) block of 384*Mp bytes, n = 64*Mp:
+//   [K^T hi: 64 x Mp u16][K^T lo: 64 x Mp u8][V hi: Mp x 64 u16][V lo: Mp x 64 u8]
+__device__ __forceinline__ uint32_t f32_to_kv24(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7Fu + ((u >> 8) & 1u);  // round to nearest even at bit 8
+  return u >> 8;
+}
+__global__ void kv24_pack_kernel(const float* __restrict__ kt, const float* __restrict__ v, int64_t n, int64_t n_bh,
+                                 uint8_t* __restrict__ out) {
+  const int64_t total4 = n_bh * n / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bh = (i * 4) / n, e = (i * 4) % n;
+    uint8_t* blk = out + bh * 6 * n;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const float4 x = *reinterpret_cast<const float4*>((which ? v : kt) + i * 4);
+      const uint32_t t0 = f32_to_kv24(x.x), t1 = f32_to_kv24(x.y), t2 = f32_to_kv24(x.z), t3 = f32_to_kv24(x.w);
+      uint2 hi;
+      hi.x = (t0 >> 8) | ((t1 >> 8) << 16);
+      hi.y = (t2 >> 8) | ((t3 >> 8) << 16);
+      const uint32_t lo = (t0 & 0xffu) | ((t1 & 0xffu) << 8) | ((t2 & 0xffu) << 16) | ((t3 & 0xffu) << 24);
+      uint8_t* base = blk + (which ? 3 * n : 0);
+      *reinterpret_cast<uint2*>(base + e * 2) = hi;
+      *reinterpret_cast<uint32_t*>(base + 2 * n + e) = lo;
+    }
+  }
+}
+void launch_kv24_pack(cudaStream_t st, const float* kt, const float* v, int B, int H, int Mp, uint8_t* out) {
+  MG_REQUIRE(Mp % 8 == 0, "kv24: memory length must be a multiple of 8");
+  const int64_t n = (int64_t)64 * Mp, n_bh = (int64_t)B * H;
+  const int blocks = (int)std::min<int64_t>((n_bh * n / 4 + 255) / 256, 148 * 16);
+  kv24_pack_kernel<<<blocks, 256, 0, st>>>(kt, v, n, n_bh, out);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// two adjacent kv24 elements from a 32-bit word of the hi plane and a (zero-extended) 16-bit word of the lo plane
+__device__ __forceinline__ float kv24_lo_elem(uint32_t hi2, uint32_t lo2) { return __uint_as_float(__byte_perm(hi2, lo2, 0x1046)); }
+__device__ __forceinline__ float kv24_hi_elem(uint32_t hi2, uint32_t lo2) { return __uint_as_float(__byte_perm(hi2, lo2, 0x3256)); }
+
+// Streaming cross-attention over kv24 blocks: same pipeline as cross_attn_stream_kernel (producer thread + ring of
+// bulk copies + 8 consumer warps); a chunk is two bulk copies (hi rows, lo rows) landing back to back in one stage.
+// Scores: thread = PAIR of adjacent keys (one 32-bit + one 16-bit shared load per pair and d-row).
+__global__ void __launch_bounds__(288) cross_attn_stream24_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kv,
+                                                                  const int* __restrict__ mask, int Mp, int H, int D,
+                                                                  float* __restrict__ ctx) {
+  constexpr int HD = 64;
+  extern __shared__ __align__(128) uint8_t smc[];
+  uint8_t* ring = smc;                                                           // [NST][CA_STAGE_BYTES]
+  float* sc = reinterpret_cast<float*>(smc + CA_NST * CA_STAGE_BYTES);           // [Mp]
+  float* sq = sc + Mp;                                                           // [64]
+  float* sred = sq + HD;                                                         // [16*64]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sred + 16 * HD);              // [NST]
+  uint64_t* empty_bar = full_bar + CA_NST;                                       // [NST]
+  float* s_b = reinterpret_cast<float*>(empty_bar + CA_NST);                     // [2 + 8]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n = (int64_t)HD * Mp;
+  const uint8_t* blk = kv + ((int64_t)b * H + h) * 6 * n;
+  const int RK = min(HD, (CA_STAGE_BYTES / (Mp * 3)) & ~1);  // d-rows per K chunk (even: both copies stay 16-byte sized)
+  const int nkc = (HD + RK - 1) / RK;
+  constexpr int VR = CA_STAGE_BYTES / (HD * 3);  // keys per V chunk
+  const int nvc = (Mp + VR - 1) / VR;
+
+  griddep_launch();
+  if (tid == 0) {
+    for (int s = 0; s < CA_NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp != 8) {
+    griddep_wait();
+    if (tid < HD) sq[tid] = q[(int64_t)b * D + h * HD + tid];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ producer (K/V were written before the loop)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < nkc + nvc; ++c) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint8_t *src_hi, *src_lo;
+        uint32_t bytes_lo;
+        if (c < nkc) {
+          const int r0 = c * RK, rows = min(RK, HD - r0);
+          src_hi = blk + (int64_t)r0 * Mp * 2;
+          src_lo = blk + 2 * n + (int64_t)r0 * Mp;
+          bytes_lo = (uint32_t)rows * Mp;
+        } else {
+          const int m0 = (c - nkc) * VR, rows = min(VR, Mp - m0);
+          src_hi = blk + 3 * n + (int64_t)m0 * HD * 2;
+          src_lo = blk + 5 * n + (int64_t)m0 * HD;
+          bytes_lo = (uint32_t)rows * HD;
+        }
+        uint8_t* dst = ring + s * CA_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], 3 * bytes_lo);
+        bulk_load_1d(dst, src_hi, 2 * bytes_lo, &full_bar[s]);
+        bulk_load_1d(dst + 2 * bytes_lo, src_lo, bytes_lo, &full_bar[s]);
+        if (++s == CA_NST) { s = 0; ph ^= 1; }
+      }
+    }
+    griddep_wait();
+    return;
+  }
+  // -------------------------------------------------------------------- consumers (256 threads)
+  int s = 0;
+  uint32_t ph = 0;
+  const int npair = Mp >> 1;
+  float acc[8];  // acc[2i], acc[2i+1] = keys 2*(tid + 256 i), +1
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int c = 0; c < nkc; ++c) {
+    mbar_wait(&full_bar[s], ph);
+    const uint8_t* buf = ring + s * CA_STAGE_BYTES;
+    const int r0 = c * RK, rows = min(RK, HD - r0);
+    const uint8_t* lo_base = buf + (size_t)rows * Mp * 2;
+    for (int rr = 0; rr < rows; ++rr) {
+      const float qd = sq[r0 + rr];
+      const uint32_t* hrow = reinterpret_cast<const uint32_t*>(buf + (size_t)rr * Mp * 2);
+      const uint16_t* lrow = reinterpret_cast<const uint16_t*>(lo_base + (size_t)rr * Mp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pi = tid + 256 * i;
+        if (pi < npair) {
+          const uint32_t h2 = hrow[pi], l2 = lrow[pi];
+          acc[2 * i] += qd * kv24_lo_elem(h2, l2);
+          acc[2 * i + 1] += qd * kv24_hi_elem(h2, l2);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (++s == CA_NST) { s = 0; ph ^= 1; }
+  }
+  // mask, max
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = 2 * (tid + 256 * (i >> 1)) + (i & 1);
+    if (m < Mp) {
+      acc[i] += (mask[(int64_t)b * Mp + m] ? 0.f : -3.4028234663852886e38f);
+      mx = fmaxf(mx, acc[i]);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_b[2 + warp] = mx;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  mx = s_b[2];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_b[2 + w]);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = 2 * (tid + 256 * (i >> 1)) + (i & 1);
+    if (m < Mp) {
+      const float pe = expf(acc[i] - mx);
+      sc[m] = pe;
+      sum += pe;
+    }
+  }
+  sum = warp_sum(sum);
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read s_b[2..9]
+  if (lane == 0) s_b[2 + warp] = sum;
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // sc[] and partial sums visible
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += s_b[2 + w];
+  const float inv = 1.f / sum;
+  // P.V: thread (r = tid/16, c = tid%16) -> 4 adjacent d of keys j == r (mod 16)
+  const int r = tid >> 4, cc = tid & 15;
+  float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < nvc; ++c) {
+    mbar_wait(&full_bar[s], ph);
+    const uint8_t* buf = ring + s * CA_STAGE_BYTES;
+    const int m0 = c * VR, rows = min(VR, Mp - m0);
+    const uint8_t* lo_base = buf + (size_t)rows * HD * 2;
+#pragma unroll
+    for (int j = 0; j < (VR + 15) / 16; ++j) {
+      const int jj = r + 16 * j;
+      if (jj < rows) {
+        const uint2 h4 = *reinterpret_cast<const uint2*>(buf + ((size_t)jj * HD + 4 * cc) * 2);
+        const uint32_t l4 = *reinterpret_cast<const uint32_t*>(lo_base + (size_t)jj * HD + 4 * cc);
+        const float pj = sc[m0 + jj];
+        a4.x += pj * __uint_as_float((h4.x << 16) | ((l4 & 0xffu) << 8));
+        a4.y += pj * __uint_as_float((h4.x & 0xffff0000u) | (l4 & 0xff00u));
+        a4.z += pj * __uint_as_float((h4.y << 16) | ((l4 >> 8) & 0xff00u));
+        a4.w += pj * __uint_as_float((h4.y & 0xffff0000u) | ((l4 >> 16) & 0xff00u));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (++s == CA_NST) { s = 0; ph ^= 1; }
+  }
+  reinterpret_cast<float4*>(sred)[r * 16 + cc] = a4;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) o += sred[rr * HD + tid];
+    ctx[(int64_t)b * D + h * HD + tid] = o * inv;
+  }
+}
+
+void launch_cross_attn_stream24(cudaStream_t st, const float* q, int B, int H, int D, const uint8_t* kv, int Mp,
+                                const int* mask, float* ctx) {
+  MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
+  MG_REQUIRE(Mp % 8 == 0 && Mp <= 2048, "cross-attention memory length must be a multiple of 8, <= 2048");
+  const size_t smem = (size_t)CA_NST * CA_STAGE_BYTES + (size_t)(Mp + 64 + 16 * 64) * 4 + 2 * CA_NST * 8 + 64;
+  static bool attr = false;
+  if (!attr) {
+    MG_CHECK_CUDA(cudaFuncSetAttribute(cross_attn_stream24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  dim3 grid(H, B);
+  launch_pdl(cross_attn_stream24_kernel, grid, dim3(288), smem, st, q, kv, mask, Mp, H, D, ctx);
+}
+
+// =====================================================================================================
 // h = relu(x) -> split planes (decode FF: the wi GEMM is split-K/atomic so the activation cannot live in its epilogue)
 __global__ void relu_split_kernel(const float* __restrict__ x, int64_t n, bf16* hi, bf16* lo) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -40,6 +40,10 @@ void launch_dec_cross_attn(cudaStream_t st, const float* q, int B, int H, int D,
 // streaming cross-attention: kt [B][H][64][Mp], v [B][H][Mp][64] (both contiguous per (b,h))
 void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int D, const float* kt, const float* v,
                               int Mp, const int* mask, float* ctx);
+// kv24 cross K/V (decode.cu): fp32 rounded to 24 significant bits, stored as a 16-bit + an 8-bit plane
+void launch_kv24_pack(cudaStream_t st, const float* kt, const float* v, int B, int H, int Mp, uint8_t* out);
+void launch_cross_attn_stream24(cudaStream_t st, const float* q, int B, int H, int D, const uint8_t* kv, int Mp,
+                                const int* mask, float* ctx);
 void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
 // part_val/part_idx: optional [B][n_part] partial maxima from the LM-head epilogue (then `logits` is only dumped)
 void launch_greedy_select(cudaStream_t st, const float* part_val, const int* part_idx, int n_part, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
@@ -97,8 +101,8 @@ struct MegaLayer {
   const float* ln[3];  // RMSNorm weights before qkv / cq / wi
   float* skb;        // self K cache [B][H][Tp/32][64][32]
   float* svb;        // self V cache [B][H][Tp][64]
-  const float* ckt;  // cross K^T [B][H][64][Mp]
-  const float* cv;   // cross V   [B][H][Mp][64]
+  const uint8_t* ckv;  // cross K/V, kv24 blocks [B][H][384 * Mp] (decode.cu)
+  const void* pad_;
 };
 struct MegaParams {
   const MegaLayer* layers;  // device array [NL]

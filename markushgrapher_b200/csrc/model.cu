@@ -190,6 +190,8 @@ struct mg_model {
   int64_t* dist_all_ids = nullptr;  // (world*B, max_length) on every rank, set per call
   // buffers of the last generate call (valid until the next encode/generate), for mg_profile_cross_attn
   std::vector<float*> prof_ckt, prof_cv;
+  std::vector<uint8_t*> prof_ckv;
+  bool prof_kv24 = false;
   float* prof_q = nullptr;
   float* prof_ctx = nullptr;
   // fused persistent decode step (decode_mega.cu): pre-swizzled weight tiles + per-layer table
@@ -316,7 +318,8 @@ struct mg_model {
   void swin_forward(cudaStream_t st, int B0, int Bc, const float* px);
   void vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_t* ids, const float* bbox, const float* px,
                    const int64_t* amask);
-  void project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv);
+  void project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv,
+                        std::vector<uint8_t*>* ckv24 = nullptr);
   void generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len, float* step_logits,
                 int32_t* steps_run, const int64_t* forced = nullptr, int forced_ld = 0);
   void generate_beam(cudaStream_t st, int B, int nb, int max_length, int64_t* out_ids, int32_t* out_len,
@@ -469,7 +472,7 @@ void mg_model::finalize(cudaStream_t st) {
         M.lin[0] = tile(L.qkv, false); M.lin[1] = tile(L.o, false); M.lin[2] = tile(L.cq, false);
         M.lin[3] = tile(L.co, false); M.lin[4] = tile(L.wi, false); M.lin[5] = tile(L.wo, false);
         M.ln[0] = L.ln1; M.ln[1] = L.ln2; M.ln[2] = L.ln3;
-        M.skb = M.svb = nullptr; M.ckt = M.cv = nullptr;
+        M.skb = M.svb = nullptr; M.ckv = nullptr; M.pad_ = nullptr;
       }
       mega_lm = tile(lm_head, true);
       mega_layers_dev = own<MegaLayer>(NL);
@@ -772,13 +775,21 @@ void mg_model::encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const 
 
 // cross K^T / V of every decoder layer, once per generate (UdopAttention :575-583). K^T [B][H][64][Mp] via operand
 // swap, V head-major [B][H][Mp][64]: every (image, head) block is one contiguous stream for the decode kernels.
-void mg_model::project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv) {
+// With ckv24 the fp32 results of a layer are repacked into kv24 blocks (decode.cu: 3 bytes per element) and the two
+// fp32 buffers are reused by the next layer.
+void mg_model::project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv,
+                                std::vector<uint8_t*>* ckv24) {
   const mg_config& c = cfg;
   const int d = c.d_model, H = c.num_heads, Mp = cur_Mp, NL = c.num_decoder_layers;
   Arena& a = scratch;
+  float *tmp_k = nullptr, *tmp_v = nullptr;
+  if (ckv24) {
+    tmp_k = a.get<float>((int64_t)B * d * Mp);
+    tmp_v = a.get<float>((int64_t)B * Mp * d);
+  }
   for (int l = 0; l < NL; ++l) {
-    ckt[l] = a.get<float>((int64_t)B * d * Mp);
-    cv[l] = a.get<float>((int64_t)B * Mp * d);
+    ckt[l] = ckv24 ? tmp_k : a.get<float>((int64_t)B * d * Mp);
+    cv[l] = ckv24 ? tmp_v : a.get<float>((int64_t)B * Mp * d);
     {
       GemmOperand A, Bop;
       A.hi = dec[l].ck.w.hi; A.lo = dec[l].ck.w.lo; A.rows = d; A.ld = dec[l].ck.ldk;
@@ -803,6 +814,11 @@ void mg_model::project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt
       launch_gemm(st, A, Bop, Mp, 64, d, H, B, 1, ep, 64);
       ++launches;
     }
+    if (ckv24) {
+      (*ckv24)[l] = a.get<uint8_t>((int64_t)B * H * 384 * Mp);
+      launch_kv24_pack(st, ckt[l], cv[l], B, H, Mp, (*ckv24)[l]);
+      ++launches;
+    }
   }
 }
 
@@ -816,12 +832,16 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   Arena& a = scratch;
   a.reset();
   // fused persistent decode step (decode_mega.cu) whenever the batch fits one activation tile
-  const bool use_mega = mega_ctas > 0 && B <= 32 && max_length <= 1024 && Mp <= 2048;
+  // cross K/V with 24 significant bits (3 bytes / element) unless MG_KV24=0
+  static const bool env_kv24 = !(getenv("MG_KV24") && getenv("MG_KV24")[0] == '0');
+  const bool kv24 = env_kv24 && Mp % 8 == 0 && Mp <= 2048;
+  const bool use_mega = mega_ctas > 0 && kv24 && B <= 32 && max_length <= 1024 && NL <= 24;
   const int Tp = (int)rup(max_length, use_mega ? 32 : 4);
   const int64_t Vld = rup(V, 4);
 
   std::vector<float*> ckt(NL), cv(NL);
-  project_cross_kv(st, B, ckt, cv);
+  std::vector<uint8_t*> ckv(NL, nullptr);
+  project_cross_kv(st, B, ckt, cv, kv24 ? &ckv : nullptr);
   // ---- decode state
   std::vector<float*> skt(NL), sv(NL);
   for (int l = 0; l < NL; ++l) {
@@ -907,8 +927,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     for (int l = 0; l < NL; ++l) {
       mega_layers[l].skb = skt[l];
       mega_layers[l].svb = sv[l];
-      mega_layers[l].ckt = ckt[l];
-      mega_layers[l].cv = cv[l];
+      mega_layers[l].ckv = ckv[l];
+      mega_layers[l].pad_ = nullptr;
     }
     MG_CHECK_CUDA(cudaMemcpyAsync(mega_layers_dev, mega_layers.data(), sizeof(MegaLayer) * NL, cudaMemcpyHostToDevice, st));
     MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, 4 * sizeof(unsigned), st));
@@ -959,8 +979,12 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       lin(0, ctx, d, L.o, x, d, nullptr, 1.f, nullptr, 0, false);  // x += o(ctx)
       // cross-attention block; zero duty: the QKV buffer just consumed by self-attention
       lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv + (int64_t)b0 * 3 * d, (int64_t)bn * 3 * d, false);
-      launch_cross_attn_stream(ls, q + (int64_t)b0 * d, bn, H, d, ckt[l] + (int64_t)b0 * d * Mp,
-                               cv[l] + (int64_t)b0 * Mp * d, Mp, mem_mask + (int64_t)b0 * Mp, ctx + (int64_t)b0 * d);
+      if (kv24)
+        launch_cross_attn_stream24(ls, q + (int64_t)b0 * d, bn, H, d, ckv[l] + (int64_t)b0 * H * 384 * Mp, Mp,
+                                   mem_mask + (int64_t)b0 * Mp, ctx + (int64_t)b0 * d);
+      else
+        launch_cross_attn_stream(ls, q + (int64_t)b0 * d, bn, H, d, ckt[l] + (int64_t)b0 * d * Mp,
+                                 cv[l] + (int64_t)b0 * Mp * d, Mp, mem_mask + (int64_t)b0 * Mp, ctx + (int64_t)b0 * d);
       lin(0, ctx, d, L.co, x, d, nullptr, 1.f, nullptr, 0, false);
       // feed-forward: RMSNorm fused into wi, ReLU fused into wo's operand load; zero duty: cross-attention q
       lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q + (int64_t)b0 * d, (int64_t)bn * d, false);
@@ -995,6 +1019,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
 
   prof_ckt = ckt;
   prof_cv = cv;
+  prof_ckv = ckv;
+  prof_kv24 = kv24;
   prof_q = q;
   prof_ctx = ctx;
   prof_bn = lanes[0].bn;
@@ -1436,8 +1462,12 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
   const int B = m->prof_bn > 0 ? m->prof_bn : m->cur_B;
   const int d = c.d_model, H = c.num_heads, Mp = m->cur_Mp, NL = (int)m->prof_ckt.size();
   auto pass = [&]() {
-    for (int l = 0; l < NL; ++l)
-      launch_cross_attn_stream(st, m->prof_q, B, H, d, m->prof_ckt[l], m->prof_cv[l], Mp, m->mem_mask, m->prof_ctx);
+    for (int l = 0; l < NL; ++l) {
+      if (m->prof_kv24)
+        launch_cross_attn_stream24(st, m->prof_q, B, H, d, m->prof_ckv[l], Mp, m->mem_mask, m->prof_ctx);
+      else
+        launch_cross_attn_stream(st, m->prof_q, B, H, d, m->prof_ckt[l], m->prof_cv[l], Mp, m->mem_mask, m->prof_ctx);
+    }
   };
   pass();  // warm-up
   MG_CHECK_CUDA(cudaEventRecord(m->ev[0], st));
@@ -1449,8 +1479,8 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
   if (ms_per_launch) *ms_per_launch = ms / (float)(reps * NL);
   // algorithmic bytes of one launch: K and V of the true memory length M (fp32), the mask, q in, ctx planes out
   if (bytes_per_launch)
-    *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->cur_M * d * 4 + (int64_t)m->cur_M * 4 + (int64_t)d * 4 +
-                                      (int64_t)d * (m->split2 ? 4 : 2));
+    *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->cur_M * d * (m->prof_kv24 ? 3 : 4) + (int64_t)m->cur_M * 4 +
+                                      (int64_t)d * 4 + (int64_t)d * (m->split2 ? 4 : 2));
   if (n_launches) *n_launches = reps * NL;
   MG_API_END
 }
