@@ -48,6 +48,7 @@ constexpr int MK_R = 32;         // activation rows (UMMA N)
 constexpr int MK_MAXSC = 2048;   // max keys of one attention row (cross: Mp, self: 2 x max_length)
 constexpr int MK_SELF_KB = 4;    // 32-key blocks per self-K chunk (32 KB)
 constexpr int MK_SELF_VR = 128;  // keys per self-V chunk (32 KB)
+constexpr int MK_SELF_NG = 4;    // self-attention items a CTA processes concurrently (2 warps each)
 constexpr int MK_CROSS_VR = 208;  // keys per cross-V chunk (kv24: 192 bytes per key, 39936 bytes per chunk)
 
 // in-kernel globaltimer stamps, profiling builds only (MG_B200_CFLAGS=-DMK_FINE, MG_MEGA_PROF=<file>);
@@ -62,6 +63,16 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 
 // mbarrier wait shared by every role (one copy in the instruction cache); bounded: a hang becomes a trap
 // (-> launch failure) instead of a dead GPU
+// watchdog diagnostics: host-mapped pinned words written just before the trap
+__device__ int* g_mk_dbg = nullptr;
+__device__ __noinline__ void mk_die(int code, uint32_t a, uint32_t b) {
+  int* d = g_mk_dbg;
+  if (d && atomicCAS(d, 0, code) == 0) {
+    d[1] = blockIdx.x; d[2] = threadIdx.x; d[3] = (int)a; d[4] = (int)b;
+    __threadfence_system();
+  }
+  __trap();
+}
 __device__ __noinline__ void mk_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
   do {
@@ -74,7 +85,7 @@ __device__ __noinline__ void mk_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();
+    if (!done && ++spins > (1u << 24)) mk_die(1, bar, parity);
   } while (!done);
 }
 __device__ __forceinline__ void mk_arrive(uint32_t bar) {
@@ -103,13 +114,16 @@ struct RingPos {
   int s = 0;
   uint32_t ph = 0;
   uint32_t xmask = 0;  // per-stage parity of the "activation tile staged" barrier (flips on linear uses only)
+  int n = 0;           // loads of this CTA's program before this position
   __device__ __forceinline__ void adv() {
     if (++s == MK_NST) { s = 0; ph ^= 1; }
+    ++n;
   }
-  __device__ __forceinline__ void adv_n(int n) {
-    const int t = s + n;
+  __device__ __forceinline__ void adv_n(int k) {
+    const int t = s + k;
     ph ^= (uint32_t)((t / MK_NST) & 1);
     s = t % MK_NST;
+    n += k;
   }
 };
 
@@ -145,13 +159,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
   uint8_t* const ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* const s_sc = reinterpret_cast<float*>(ring + MK_OFF_SC);
   float* const s_q = reinterpret_cast<float*>(ring + MK_OFF_SQ);
-  float* const s_new = reinterpret_cast<float*>(ring + MK_OFF_SNEW);
   float* const s_red = reinterpret_cast<float*>(ring + MK_OFF_SRED);
   float* const s_rs = reinterpret_cast<float*>(ring + MK_OFF_RS);
   float* const s_part = reinterpret_cast<float*>(ring + MK_OFF_PART);
   int* const s_pi = reinterpret_cast<int*>(ring + MK_OFF_PI);
   float* const s_b = reinterpret_cast<float*>(ring + MK_OFF_SB);
   volatile int* const s_phase = reinterpret_cast<volatile int*>(ring + MK_OFF_SB + 32);
+  volatile int* const s_issued = reinterpret_cast<volatile int*>(ring + MK_OFF_SB + 36);  // loads the producer has issued
   const uint32_t ring_a = smem_u32(ring);
   const uint32_t bar_full = ring_a + MK_OFF_BAR, bar_empty = bar_full + 8 * MK_NST, bar_xrdy = bar_empty + 8 * MK_NST;
   const uint32_t bar_tfull = bar_xrdy + 8 * MK_NST, bar_tempty = bar_tfull + 8;
@@ -177,10 +191,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
       mbar_init(reinterpret_cast<uint64_t*>(ring + MK_OFF_BAR) + 2 * MK_NST + s, 128);
     }
     mbar_init(reinterpret_cast<uint64_t*>(ring + MK_OFF_BAR) + 3 * MK_NST, 1);
-    mbar_init(reinterpret_cast<uint64_t*>(ring + MK_OFF_BAR) + 3 * MK_NST + 1, 128);
+    mbar_init(reinterpret_cast<uint64_t*>(ring + MK_OFF_BAR) + 3 * MK_NST + 1, 256);
     *s_phase = 0;  // phase the consumers have entered (prefetch gate)
+    *s_issued = 0;
     fence_mbar_init();
     if (g == 0) p.bar_ctr[(step + 1) & 1] = 0u;  // the other parity's counter is idle during this launch
+    if (g == 0) g_mk_dbg = p.dbg_host;
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 32);
@@ -198,7 +214,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
   const int cross_rk = min(64, (MK_STAGE / (Mp * 3)) & ~1);  // d-rows per K chunk, even (16-byte sized copies)
   const int cross_nkc = (64 + cross_rk - 1) / cross_rk;
   const int cross_nvc = (Mp + MK_CROSS_VR - 1) / MK_CROSS_VR;
-  const int my_attn = items_of_cta(n_attn, g, G);
+  // attention items are spread over Ga <= G CTAs so that every one of them gets the same count (512 items over 148
+  // CTAs would be 3 or 4 each and the phase would run at the pace of 4; over 128 CTAs it is exactly 4 each and HBM,
+  // not the SM count, stays the limit)
+  const int Ga = (n_attn + (n_attn + G - 1) / G - 1) / ((n_attn + G - 1) / G);
+  const int my_attn = g < Ga ? items_of_cta(n_attn, g, Ga) : 0;
+  const int attn_first = g < Ga ? g : n_attn;
   const int Tb = p.Tp >> 5;  // 32-key blocks per (image, head) of the self K cache
 
   if (warp == 0) {
@@ -230,7 +251,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               const int want = l * 8 + ph;
               const long long t0 = clock64();
               while (*s_phase < want)
-                if (clock64() - t0 > 4000000000LL) __trap();
+                if (clock64() - t0 > 4000000000LL) mk_die(2, want, *s_phase);
             }
             n_items = n_attn;
             if (ph == 1) {
@@ -251,39 +272,47 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             base0 = W.w; sa0 = (size_t)W.num_kb * MK_WTILE; sb0 = (size_t)W.kb_per_item * MK_WTILE;
             tot0 = 0; chunk0 = MK_WTILE;
           }
-          for (int it = g; it < n_items; it += G) {
-            const int major = it / div, minor = it - major * div;
+          // items are issued in bundles: the self-attention phase processes MK_SELF_NG items concurrently, so their
+          // chunks are interleaved (chunk c of every item of the bundle, then chunk c+1, ...); elsewhere bundle = 1
+          const int stride = attn ? Ga : G;
+          const int bundle = (attn && ph == 1) ? MK_SELF_NG : 1;
+          for (int it0 = attn ? attn_first : g; it0 < n_items; it0 += stride * bundle) {
             for (int sidx = 0; sidx < 2; ++sidx) {
-              const uint8_t* src = sidx ? base1 + major * sa1 : base0 + major * sa0 + minor * sb0;
-              uint32_t left = sidx ? tot1 : (attn ? tot0 : (uint32_t)min(upi, units - minor * upi) * MK_WTILE);
+              if (sidx && !base1) break;
               const uint32_t chunk = sidx ? chunk1 : chunk0;
-              if (sidx && !base1) left = 0;
-              const uint8_t* const src0 = src;
-              while (left) {
-                const uint32_t bytes = min(left, chunk);
-                // cap the loads this SM keeps in flight (a deeper queue adds latency, not bandwidth)
-                if (n_put >= max_inflight) {
-                  const int m = n_put - max_inflight;
-                  mk_wait(bar_full + 8 * (m % MK_NST), (uint32_t)((m / MK_NST) & 1));
-                }
-                ++n_put;
-                mk_wait(bar_empty + 8 * r.s, r.ph ^ 1);
-                const uint32_t fb = bar_full + 8 * r.s;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(lo_off ? bytes + (bytes >> 1) : bytes) : "memory");
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                        ring_a + (uint32_t)r.s * MK_STAGE),
-                    "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(fb), "l"(pol_stream)
-                    : "memory");
-                if (lo_off)
+              const int minor0 = it0 % div;
+              const uint32_t tot = sidx ? tot1 : (attn ? tot0 : (uint32_t)min(upi, units - minor0 * upi) * MK_WTILE);
+              for (uint32_t off = 0; off < tot; off += chunk) {
+                const uint32_t bytes = min(chunk, tot - off);
+                for (int gi = 0; gi < bundle; ++gi) {
+                  const int it = it0 + gi * stride;
+                  if (it >= n_items) break;
+                  const int major = it / div, minor = it - major * div;
+                  const uint8_t* const src0 = sidx ? base1 + major * sa1 : base0 + major * sa0 + minor * sb0;
+                  // cap the loads this SM keeps in flight (a deeper queue adds latency, not bandwidth)
+                  if (n_put >= max_inflight) {
+                    const int m = n_put - max_inflight;
+                    mk_wait(bar_full + 8 * (m % MK_NST), (uint32_t)((m / MK_NST) & 1));
+                  }
+                  ++n_put;
+                  mk_wait(bar_empty + 8 * r.s, r.ph ^ 1);
+                  const uint32_t fb = bar_full + 8 * r.s;
+                  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(lo_off ? bytes + (bytes >> 1) : bytes) : "memory");
                   asm volatile(
                       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                          ring_a + (uint32_t)r.s * MK_STAGE + bytes),
-                      "l"(reinterpret_cast<uint64_t>(src0 + lo_off + ((src - src0) >> 1))), "r"(bytes >> 1), "r"(fb), "l"(pol_stream)
+                          ring_a + (uint32_t)r.s * MK_STAGE),
+                      "l"(reinterpret_cast<uint64_t>(src0 + off)), "r"(bytes), "r"(fb), "l"(pol_stream)
                       : "memory");
-                r.adv();
-                src += bytes;
-                left -= bytes;
+                  if (lo_off)
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                            ring_a + (uint32_t)r.s * MK_STAGE + bytes),
+                        "l"(reinterpret_cast<uint64_t>(src0 + lo_off + (off >> 1))), "r"(bytes >> 1), "r"(fb), "l"(pol_stream)
+                        : "memory");
+                  r.adv();
+                  __threadfence_block();
+                  *s_issued = n_put;
+                }
               }
             }
           }
@@ -367,95 +396,161 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // ---------------------------------------------------------------------------------- self-attention
           // fused KV-cache append + single-query attention with the T5 unidirectional bucket bias (no 1/sqrt(d)).
           // K cache [b][h][key/32][64 d][32 keys] (contiguous per (image, head), conflict-free thread = key),
-          // V cache [b][h][key][64 d].
-          for (int it = g; it < n_attn; it += G) {
-            const int b = it / H, h = it - b * H;
-            if (ct < 64) {
-              const float* qp = p.qkv + (int64_t)b * 3 * D + h * 64 + ct;
-              const float qv = __ldcg(qp), kn = __ldcg(qp + D), vn = __ldcg(qp + 2 * D);
-              s_q[ct] = qv;
-              s_new[ct] = vn;
-              L.skb[(size_t)it * Tb * 2048 + (size_t)(step >> 5) * 2048 + ct * 32 + (step & 31)] = kn;  // append
-              L.svb[((size_t)it * p.Tp + step) * 64 + ct] = vn;
-              s_red[ct] = qv * kn;
-            }
-            cons_sync();
-            for (int c = 0; c < self_nkc; ++c) {
-              mk_wait(bar_full + 8 * r.s, r.ph);
-              const float* buf = reinterpret_cast<const float*>(ring + (size_t)r.s * MK_STAGE);
-              const int nb = min(MK_SELF_KB, self_nblk - c * MK_SELF_KB);
-              const int blk = cw & 3, dh = cw >> 2;  // warp -> (key block, d half): two partial sums per key
-              if (blk < nb) {
-                const float* kp = buf + blk * 2048 + dh * 1024 + lane;
-                const float* qh = s_q + dh * 32;
-                float a = 0.f;
+          // V cache [b][h][key][64 d].  An item is small and its chain of dependent steps long, so the CTA works on
+          // MK_SELF_NG items at once: one pair of warps per item, synchronised by its own named barrier; the
+          // producer interleaves the items' chunks in the ring (chunk c of item gi sits c * ng + gi loads ahead).
+          const int gi = cw >> 1, t = ct & 63, w2 = cw & 1;
+          float* const sc_g = s_sc + gi * 512;                      // probabilities of this group's item (Tp <= 512)
+          float* const q_g = s_red + gi * 192;                      // q [64] | new v [64] | scratch [64]
+          float* const vn_g = q_g + 64;
+          float* const red_g = q_g + 128;
+          const int nch = self_nkc + self_nvc;
+          auto gsync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + gi) : "memory"); };
+          for (int k0 = 0; k0 < my_attn; k0 += MK_SELF_NG) {
+            const int ng = min(MK_SELF_NG, my_attn - k0);
+            if (gi < ng) {
+              const int it = attn_first + (k0 + gi) * Ga;
+              const int b = it / H, h = it - b * H;
+              {
+                const float* qp = p.qkv + (int64_t)b * 3 * D + h * 64 + t;
+                const float rsb = __ldcg(p.rs + b);  // RMSNorm row scale deferred from the qkv projection
+                const float qv = __ldcg(qp) * rsb, kn = __ldcg(qp + D) * rsb, vn = __ldcg(qp + 2 * D) * rsb;
+                q_g[t] = qv;
+                vn_g[t] = vn;
+                red_g[t] = qv * kn;
+                L.skb[(size_t)it * Tb * 2048 + (size_t)(step >> 5) * 2048 + t * 32 + (step & 31)] = kn;  // append
+                L.svb[((size_t)it * p.Tp + step) * 64 + t] = vn;
+              }
+              float bias8[8];  // T5 bucket bias of this thread's keys j = t + 64 i (two dependent global loads each)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int j = t + 64 * i;
+                bias8[i] = j <= step ? p.dec_bias[p.lut[step - j] * H + h] : 0.f;
+              }
+              gsync();
+              // scores over the cached keys stay in registers: the thread that scores key j also owns it below
+              float s8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c < self_nkc) {
+                  const int pos = r.s + c * ng + gi;
+                  const int st = pos % MK_NST;
+                  const uint32_t par = r.ph ^ (uint32_t)((pos / MK_NST) & 1);
+                  // The groups drift apart and bulk copies land out of order, so this stage's PREVIOUS load (another
+                  // group's) may still be in flight, and a parity wait two phases ahead would alias.  The producer
+                  // issues a load only after the stage's previous occupant has landed and been consumed, so first
+                  // wait until this load has been issued, then for it to land.
+                  {
+                    const int seq = r.n + c * ng + gi;
+                    uint32_t spins = 0;
+                    while (*s_issued <= seq)
+                      if (++spins > (1u << 26)) mk_die(4, (uint32_t)seq, (uint32_t)*s_issued);
+                  }
+                  mk_wait(bar_full + 8 * st, par);
+                  const float* buf = reinterpret_cast<const float*>(ring + (size_t)st * MK_STAGE);
+                  const int nb = min(MK_SELF_KB, self_nblk - c * MK_SELF_KB);
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const int blk = w2 + 2 * u;
+                    if (blk < nb) {
+                      const float* kp = buf + blk * 2048 + lane;
+                      float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
-                for (int d = 0; d < 32; ++d) a += qh[d] * kp[d * 32];
-                s_sc[dh * 1024 + (c * MK_SELF_KB + blk) * 32 + lane] = a;  // second halves at sc[1024..] (Tp <= 1024)
+                      for (int d = 0; d < 64; d += 2) {
+                        a0 += q_g[d] * kp[d * 32];
+                        a1 += q_g[d + 1] * kp[d * 32 + 32];
+                      }
+                      s8[c * 2 + u] = a0 + a1;
+                    }
+                  }
+                  gsync();
+                  if (t == 0) mk_arrive(bar_empty + 8 * st);
+                }
               }
-              cons_sync();
-              if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
-              r.adv();
-            }
-            float mx = -INFINITY;
-            for (int j = ct; j <= step; j += 256) {
-              float sv;
-              if (j < step) {
-                sv = s_sc[j] + s_sc[1024 + j];
-              } else {
-                sv = 0.f;
-                for (int d = 0; d < 64; ++d) sv += s_red[d];
+              float snew = 0.f;  // score of the token being appended
+#pragma unroll 8
+              for (int d = 0; d < 64; ++d) snew += red_g[d];
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int j = t + 64 * i;
+                s8[i] = j < step ? s8[i] + bias8[i] : (j == step ? snew + bias8[i] : -INFINITY);
+                mx = fmaxf(mx, s8[i]);
               }
-              sv += p.dec_bias[p.lut[step - j] * H + h];
-              s_sc[j] = sv;
-              mx = fmaxf(mx, sv);
-            }
-            mx = mk_block_reduce(mx, s_b, cw, lane, 1);
-            float sum = 0.f;
-            for (int j = ct; j <= step; j += 256) {
-              const float e = expf(s_sc[j] - mx);
-              s_sc[j] = e;
-              sum += e;
-            }
-            sum = mk_block_reduce(sum, s_b, cw, lane, 0);  // also publishes sc[]
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = 0; c < self_nvc; ++c) {
-              mk_wait(bar_full + 8 * r.s, r.ph);
-              const float4* buf4 = reinterpret_cast<const float4*>(ring + (size_t)r.s * MK_STAGE);
-              const int m0 = c * MK_SELF_VR, rows = min(MK_SELF_VR, step - m0);
-#pragma unroll 2
-              for (int jj = r16; jj < rows; jj += 16) {
-                const float4 vv = buf4[jj * 16 + c16];
-                const float pj = s_sc[m0 + jj];
-                acc.x += pj * vv.x; acc.y += pj * vv.y; acc.z += pj * vv.z; acc.w += pj * vv.w;
+              mx = warp_max(mx);
+              if (lane == 0) s_b[gi * 2 + w2] = mx;
+              gsync();
+              mx = fmaxf(s_b[gi * 2], s_b[gi * 2 + 1]);
+              float sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int j = t + 64 * i;
+                if (j <= step) {
+                  const float e = expf(s8[i] - mx);
+                  sc_g[j] = e;
+                  sum += e;
+                }
               }
-              cons_sync();
-              if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
-              r.adv();
-            }
-            if (r16 == 0) {
-              const float pj = s_sc[step];
-              acc.x += pj * s_new[4 * c16]; acc.y += pj * s_new[4 * c16 + 1];
-              acc.z += pj * s_new[4 * c16 + 2]; acc.w += pj * s_new[4 * c16 + 3];
-            }
-            cons_sync();
-            reinterpret_cast<float4*>(s_red)[r16 * 16 + c16] = acc;
-            cons_sync();
-            if (ct < 64) {
-              float o = 0.f;
+              sum = warp_sum(sum);
+              gsync();  // both warps have read the maxima
+              if (lane == 0) s_b[gi * 2 + w2] = sum;
+              gsync();  // probabilities and partial sums visible
+              sum = s_b[gi * 2] + s_b[gi * 2 + 1];
+              // P.V: thread (r4 = t / 16, c = t % 16) -> float4 column c over keys j == r4 (mod 4)
+              const int r4 = t >> 4, cc = t & 15;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c < self_nvc) {
+                  const int pos = r.s + (self_nkc + c) * ng + gi;
+                  const int st = pos % MK_NST;
+                  const uint32_t par = r.ph ^ (uint32_t)((pos / MK_NST) & 1);
+                  {
+                    const int seq = r.n + (self_nkc + c) * ng + gi;
+                    uint32_t spins = 0;
+                    while (*s_issued <= seq)
+                      if (++spins > (1u << 26)) mk_die(4, (uint32_t)seq, (uint32_t)*s_issued);
+                  }
+                  mk_wait(bar_full + 8 * st, par);
+                  const float4* buf4 = reinterpret_cast<const float4*>(ring + (size_t)st * MK_STAGE);
+                  const int m0 = c * MK_SELF_VR, rows = min(MK_SELF_VR, step - m0);
 #pragma unroll 4
-              for (int rr = 0; rr < 16; ++rr) o += s_red[rr * 64 + ct];
-              p.ctx[(int64_t)b * D + h * 64 + ct] = o / sum;
+                  for (int jj = r4; jj < rows; jj += 4) {
+                    const float4 vv = buf4[jj * 16 + cc];
+                    const float pj = sc_g[m0 + jj];
+                    acc.x += pj * vv.x; acc.y += pj * vv.y; acc.z += pj * vv.z; acc.w += pj * vv.w;
+                  }
+                  gsync();
+                  if (t == 0) mk_arrive(bar_empty + 8 * st);
+                }
+              }
+              // combine the four key residues: lanes l and l+16 inside a warp, then the two warps through shared memory
+              acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+              acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+              if (w2 == 1 && lane < 16) reinterpret_cast<float4*>(red_g)[lane] = acc;
+              gsync();
+              if (w2 == 0 && lane < 16) {
+                const float4 o2 = reinterpret_cast<const float4*>(red_g)[lane];
+                const float4 vn4 = reinterpret_cast<const float4*>(vn_g)[lane];
+                const float pn = sc_g[step], inv = 1.f / sum;
+                float4 o;
+                o.x = (acc.x + o2.x + pn * vn4.x) * inv; o.y = (acc.y + o2.y + pn * vn4.y) * inv;
+                o.z = (acc.z + o2.z + pn * vn4.z) * inv; o.w = (acc.w + o2.w + pn * vn4.w) * inv;
+                *reinterpret_cast<float4*>(p.ctx + (int64_t)b * D + h * 64 + 4 * lane) = o;
+              }
+              gsync();  // this group's shared scratch is reusable
             }
-            cons_sync();  // sq / snew / sred / sc reusable
+            r.adv_n(nch * ng);
           }
         } else if (l < NL && ph == 4) {
           // ---------------------------------------------------------------------------------- cross-attention
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
           // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = pair of adjacent keys.
-          for (int it = g; it < n_attn; it += G) {
+          for (int it = attn_first; it < n_attn; it += Ga) {
             const int b = it / H, h = it - b * H;
-            if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct);
+            if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct) * __ldcg(p.rs + MK_R + b);
             int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
 #pragma unroll
             for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
@@ -538,36 +633,43 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           }
         } else {
           // ---------------------------------------------------------------------------------- linear
-          // out[b][n] (+)= rs[b] * sum_k pro(x)[b][k] * W[n][k];  pro: 0 none, 1 RMSNorm (x*lnw staged, rs in the
-          // epilogue), 2 ReLU.  (input, prologue, output, which buffer this phase zeroes for a later one):
-          int pro = 1, ldx = D, ld_out = D;
+          // out[b][n] (+)= sum_k pro(x)[b][k] * W[n][k];  pro: 0 none, 1 RMSNorm weight (x*lnw staged; the row scale
+          // rs[b] = rsqrt(mean(x^2)+eps) is NOT applied here: it is computed off the critical path by one warp per
+          // image, published through p.rs, and applied by the consumer of this phase's output -- q/k/v and the
+          // cross query when they are loaded, the FF hidden activations as relu(rs*h) = rs*relu(h)), 2 ReLU * rs.
+          // LM head only: rs * d_model^-0.5 applied in the epilogue (the logits are the final output).
+          // (input, prologue, output, which buffer this phase zeroes for a later one):
+          int pro = 1, ldx = D, ld_out = D, rs_slot = -1;
           const float* x = p.x;
           float* out = p.x;
           const float* lnw = nullptr;
-          float scale = 1.f;
           float* zero_ptr = nullptr;
           int64_t zero_n = 0;
-          bool store = false;
-          if (l == NL) {  // LM head: final RMSNorm * d_model^-0.5 fused, direct store + per-tile argmax
-            lnw = p.final_ln; scale = p.logit_scale; out = p.logits; ld_out = p.ld_logits; store = true;
+          const bool store = l == NL;
+          if (store) {  // LM head: final RMSNorm * d_model^-0.5 fused, direct store + per-tile argmax
+            lnw = p.final_ln; out = p.logits; ld_out = p.ld_logits;
           } else if (ph == 0) {  // x -> qkv (RMSNorm ln1); zero: FF hidden buffer
-            lnw = L.ln[0]; out = p.qkv; ld_out = 3 * D; zero_ptr = p.hbuf; zero_n = (int64_t)B * p.DFF;
+            lnw = L.ln[0]; out = p.qkv; ld_out = 3 * D; zero_ptr = p.hbuf; zero_n = (int64_t)B * p.DFF; rs_slot = 0;
           } else if (ph == 2 || ph == 5) {  // ctx -> x (+=): attention output projections
             pro = 0; x = p.ctx;
           } else if (ph == 3) {  // x -> q (RMSNorm ln2); zero: qkv
-            lnw = L.ln[1]; out = p.q; zero_ptr = p.qkv; zero_n = (int64_t)B * 3 * D;
+            lnw = L.ln[1]; out = p.q; zero_ptr = p.qkv; zero_n = (int64_t)B * 3 * D; rs_slot = 1;
           } else if (ph == 6) {  // x -> hidden (RMSNorm ln3); zero: q
-            lnw = L.ln[2]; out = p.hbuf; ld_out = p.DFF; zero_ptr = p.q; zero_n = (int64_t)B * D;
-          } else {  // ph == 7: relu(hidden) -> x (+=)
+            lnw = L.ln[2]; out = p.hbuf; ld_out = p.DFF; zero_ptr = p.q; zero_n = (int64_t)B * D; rs_slot = 2;
+          } else {  // ph == 7: rs * relu(hidden) -> x (+=)
             pro = 2; x = p.hbuf; ldx = p.DFF;
           }
           const MegaLin& W = l < NL ? L.lin[mega_lin_of_phase(ph)] : p.lm_head;
           const int items = W.tiles * W.ksplit;
+#ifdef MK_FINE
+          unsigned long long* fine = (p.prof && ct == 0 && phase_i >= 8 && phase_i < 16) ? p.prof + ((size_t)g * 512 + 256 + (phase_i - 8) * 16) * 2 : nullptr;
+#endif
+          MK_STAMP(fine, 0);
           if (!is_worker) {
-            // ---- statistic warps: RMSNorm row scale of all 32 rows (warp wq owns rows 8 wq .. 8 wq + 7)
             const int t = ct - 128, wq = cw - 4;
-            if (g < items) {
-              if (pro == 1) {
+            if (store) {
+              // LM head: every CTA needs the scale of all 32 rows in its epilogue (warp wq owns rows 8 wq .. 8 wq + 7)
+              if (g < items) {
                 const int n4 = W.K >> 2;
 #pragma unroll 1
                 for (int rp = 0; rp < 8; rp += 2) {
@@ -587,42 +689,47 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                       ss += (lane + 32 * i < n4) ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f;
                     }
                     ss = warp_sum(ss);
-                    if (lane == 0) s_rs[wq * 8 + rp + u] = rsqrtf(ss / (float)W.K + p.eps) * scale;
+                    if (lane == 0) s_rs[wq * 8 + rp + u] = rsqrtf(ss / (float)W.K + p.eps) * p.logit_scale;
                   }
                 }
-              } else if (t < MK_R) {
-                s_rs[t] = scale;
+              }
+            } else {
+              if (rs_slot >= 0 && wq == 0 && g < B) {
+                // RMSNorm row scale of image g, consumed one phase later (by other CTAs) through p.rs
+                const int n4 = W.K >> 2;
+                const float* xr = x + (int64_t)g * ldx;
+                float4 qa[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qa[i] = ldcg4(xr + 4 * min(lane + 32 * i, n4 - 1));
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  ss += (lane + 32 * i < n4) ? (qa[i].x * qa[i].x + qa[i].y * qa[i].y) + (qa[i].z * qa[i].z + qa[i].w * qa[i].w) : 0.f;
+                ss = warp_sum(ss);
+                if (lane == 0) p.rs[rs_slot * MK_R + g] = rsqrtf(ss / (float)W.K + p.eps);
+              }
+              if (zero_ptr) {  // zero duty while the workers stage
+                float4* z4 = reinterpret_cast<float4*>(zero_ptr);
+                for (int64_t i = (int64_t)g * 128 + t; i < (zero_n >> 2); i += (int64_t)G * 128) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
             }
-#ifdef MK_FINE
-            unsigned long long* fs = (p.prof && ct == 128 && phase_i >= 8 && phase_i < 16) ? p.prof + ((size_t)g * 512 + 256 + (phase_i - 8) * 16) * 2 : nullptr;
-            MK_STAMP(fs, 10);
-#endif
-            cons_sync();  // row scales published (the workers wait here before their first epilogue)
-            if (zero_ptr) {  // zero duty, off the critical path (completes before this phase's grid barrier)
-              float4* z4 = reinterpret_cast<float4*>(zero_ptr);
-              for (int64_t i = (int64_t)g * 128 + t; i < (zero_n >> 2); i += (int64_t)G * 128) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            // keep this warp's view of the ring in step with the k-blocks the workers / MMA warp consume
-            for (int it = g; it < items; it += G) {
-              int tile, kb0;
-              r.adv_n(lin_item_kbs(W, it, tile, kb0));
-            }
-          } else {
-            // ---- workers (128 threads): stage the activation tiles, then the TMEM epilogue
-            const int c4 = ct & 15, r8 = ct >> 4;
-            const float relu_lo = (pro == 2) ? 0.f : -INFINITY;
-            bool first = true;
-#ifdef MK_FINE
-            unsigned long long* fine = (p.prof && ct == 0 && phase_i >= 8 && phase_i < 16) ? p.prof + ((size_t)g * 512 + 256 + (phase_i - 8) * 16) * 2 : nullptr;
-#endif
-            MK_STAMP(fine, 0);
-            for (int it = g; it < items; it += G) {
-              int tile, kb0;
-              const int nkb = lin_item_kbs(W, it, tile, kb0);
+          }
+          const int c4 = ct & 15, r8 = (ct & 127) >> 4;
+          const float relu_lo = (pro == 2) ? 0.f : -INFINITY;
+          bool first = true;
+          for (int it = g; it < items; it += G) {
+            int tile, kb0;
+            const int nkb = lin_item_kbs(W, it, tile, kb0);
+            if (is_worker) {
+              // ---- stage the activation tiles of this item's k-blocks (128 threads)
               const float* xk = x + kb0 * 64 + c4 * 4;
               float4 v[4], gw = make_float4(1.f, 1.f, 1.f, 1.f);
               if (pro == 1) gw = *reinterpret_cast<const float4*>(lnw + kb0 * 64 + c4 * 4);
+              float rsr[4] = {1.f, 1.f, 1.f, 1.f};
+              if (pro == 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rsr[i] = __ldcg(p.rs + 2 * MK_R + min(r8 + i * 8, B - 1));
+              }
 #pragma unroll
               for (int i = 0; i < 4; ++i) v[i] = ldcg4(xk + (int64_t)min(r8 + i * 8, B - 1) * ldx);
 #pragma unroll 1
@@ -640,8 +747,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                   const int rr = r8 + i * 8;
                   float4 w = v[i];
                   if (rr >= B) w = make_float4(0.f, 0.f, 0.f, 0.f);
-                  w.x = fmaxf(w.x, relu_lo) * gw.x; w.y = fmaxf(w.y, relu_lo) * gw.y;
-                  w.z = fmaxf(w.z, relu_lo) * gw.z; w.w = fmaxf(w.w, relu_lo) * gw.w;
+                  const float gx = gw.x * rsr[i], gy = gw.y * rsr[i], gz = gw.z * rsr[i], gq = gw.w * rsr[i];
+                  w.x = fmaxf(w.x, relu_lo) * gx; w.y = fmaxf(w.y, relu_lo) * gy;
+                  w.z = fmaxf(w.z, relu_lo) * gz; w.w = fmaxf(w.w, relu_lo) * gq;
                   // fp32 -> bf16 hi + bf16 lo (x ~= hi + lo), two elements per conversion
                   const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
                   const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
@@ -663,36 +771,55 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                 for (int i = 0; i < 4; ++i) v[i] = vn[i];
                 gw = gn;
               }
-              MK_STAMP(fine, 2);
-              if (first) {
-                cons_sync();  // row scales from the statistic warps
-                first = false;
-              }
-              MK_STAMP(fine, 3);
-              // ---- epilogue: TMEM -> registers in 8-column chunks (thread = output feature, column = image)
-              mk_wait(bar_tfull, n_item & 1);
-              MK_STAMP(fine, 4);
-              tc_fence_after();
-              const int q = warp & 3;
-              const int n = tile * 128 + q * 32 + lane;
-              const bool n_ok = n < W.N;
-              float* o = out + n;
-              const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-              if (!store) {
-                // split-K partial sums: red.global.add into the next buffer / the residual stream (the hot path)
+            } else {
+              r.adv_n(nkb);  // keep this warp's view of the ring in step with the workers / the MMA warp
+            }
+            MK_STAMP(fine, 2);
+            if (store && first) cons_sync();  // LM head: row scales from the statistic warps
+            first = false;
+            // ---- epilogue: TMEM -> registers (thread = output feature, column = image)
+            mk_wait(bar_tfull, n_item & 1);
+            MK_STAMP(fine, 4);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int n = tile * 128 + q * 32 + lane;
+            const bool n_ok = n < W.N;
+            if (!store) {
+              // split-K partial sums: red.global.add into the next buffer / the residual stream.  All 8 consumer
+              // warps take part: two warps per TMEM lane quadrant, 16 of the 32 image columns each (this loop runs
+              // with one warp per scheduler, so its length in instructions is what the phase waits for).
+              const int c_lo = (cw >> 2) * 16;
+              const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c_lo;
+              float* op = out + (int64_t)c_lo * ld_out + n;
 #pragma unroll 1
-                for (int c0 = 0; c0 < MK_R; c0 += 8) {
-                  uint32_t rr[8];
-                  tmem_ld_32x32_x8(taddr + c0, rr);
-                  tmem_ld_wait();
+              for (int c = 0; c < 2; ++c) {
+                uint32_t rr[8];
+                tmem_ld_32x32_x8(taddr + c * 8, rr);
+                tmem_ld_wait();
+                const int nv = B - (c_lo + c * 8);  // image rows left (warp-uniform)
+                if (n_ok) {
+                  if (nv >= 8) {
+                    float* pj = op;
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (n_ok && c0 + j < B) atomicAdd(o + (int64_t)(c0 + j) * ld_out, __uint_as_float(rr[j]) * s_rs[c0 + j]);
+                    for (int j = 0; j < 8; ++j) {
+                      atomicAdd(pj, __uint_as_float(rr[j]));
+                      pj += ld_out;
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                      if (j < nv) atomicAdd(op + (int64_t)j * ld_out, __uint_as_float(rr[j]));
+                  }
                 }
-                tc_fence_before();
-                mk_arrive(bar_tempty);
-              } else {
-                // LM head (once per step): direct store + per-row (max, first argmax) over this tile's features
+                op += (int64_t)8 * ld_out;
+              }
+              tc_fence_before();
+              mk_arrive(bar_tempty);
+            } else {
+              // LM head (once per step, worker warps only): scaled direct store + per-row (max, first argmax)
+              if (is_worker) {
+                float* o = out + n;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
                 for (int c0 = 0; c0 < MK_R; c0 += 8) {
                   uint32_t rr[8];
@@ -714,8 +841,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                     }
                   }
                 }
-                tc_fence_before();
-                mk_arrive(bar_tempty);
+              }
+              tc_fence_before();
+              mk_arrive(bar_tempty);
+              if (is_worker) {
                 asm volatile("bar.sync 3, 128;" ::: "memory");
                 if (ct < B) {
                   float bv = s_part[ct * 4];
@@ -731,11 +860,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                 }
                 asm volatile("bar.sync 3, 128;" ::: "memory");  // s_part reusable by the next item
               }
-              MK_STAMP(fine, 5);
-              ++n_item;
             }
-            if (first) cons_sync();
+            MK_STAMP(fine, 5);
+            ++n_item;
           }
+          if (store && first) cons_sync();
         }
         if (l == NL) break;
         // ------------------------------------------------------------------------------------ grid barrier
@@ -753,7 +882,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
             if (v >= bar_target) break;
-            if (clock64() - t0 > 4000000000LL) __trap();
+            if (clock64() - t0 > 4000000000LL) mk_die(3, v, bar_target);
           }
           MK_STAMP(ps, 1);
           *s_phase = phase_i + 1;  // consumers enter the next phase (releases the producer's prefetch gate)
@@ -830,7 +959,7 @@ int mega_max_ctas() {
 
 void launch_decode_step(cudaStream_t st, const MegaParams& p, int n_ctas) {
   MG_REQUIRE(p.B >= 1 && p.B <= MK_R, "fused decode step: 1 <= B <= 32");
-  MG_REQUIRE(p.Mp % 8 == 0 && p.Mp <= MK_MAXSC && p.Tp % 32 == 0 && p.Tp <= 1024, "fused decode step: Mp / max_length out of range");
+  MG_REQUIRE(p.Mp % 8 == 0 && p.Mp <= MK_MAXSC && p.Tp % 32 == 0 && p.Tp <= 512, "fused decode step: Mp / max_length out of range");
   MG_REQUIRE(p.D == p.H * 64 && p.D <= 1024 && p.D % 64 == 0 && p.DFF % 64 == 0, "fused decode step: unsupported dims");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_ctas);

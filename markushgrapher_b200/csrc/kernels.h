@@ -119,8 +119,10 @@ struct MegaParams {
   const int* mem_mask;
   const float* dec_bias;
   const int* lut;
+  float* rs;          // [3][32] RMSNorm row scales published by the qkv / cq / wi phases for their consumers
   unsigned* bar_ctr;  // [2], zero before the first step
   int gate = 1;          // 1: attention K/V streams wait until the consumers enter their phase
+  int* dbg_host = nullptr;  // host-mapped pinned words for the watchdog's diagnostics (may be null)
   int dbg = 0;           // profiling builds (-DMK_FINE) only: 1 = skip the reductions, 2 = skip the TMEM loads
   int max_inflight = 5;  // bulk loads one SM keeps in flight (<= ring stages)
   unsigned long long* prof = nullptr;  // debug: [CTAs][256][2] globaltimer at (work done, barrier passed) per phase

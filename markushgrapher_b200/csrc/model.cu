@@ -835,7 +835,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   // cross K/V with 24 significant bits (3 bytes / element) unless MG_KV24=0
   static const bool env_kv24 = !(getenv("MG_KV24") && getenv("MG_KV24")[0] == '0');
   const bool kv24 = env_kv24 && Mp % 8 == 0 && Mp <= 2048;
-  const bool use_mega = mega_ctas > 0 && kv24 && B <= 32 && max_length <= 1024 && NL <= 24;
+  const bool use_mega = mega_ctas > 0 && kv24 && B <= 32 && max_length <= 512 && NL <= 24;
   const int Tp = (int)rup(max_length, use_mega ? 32 : 4);
   const int64_t Vld = rup(V, 4);
 
@@ -939,6 +939,9 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     mp.x = x; mp.qkv = qkv; mp.q = q; mp.ctx = ctx; mp.hbuf = hbuf; mp.logits = logits; mp.ld_logits = (int)Vld;
     mp.part_val = part_val; mp.part_idx = part_idx; mp.step_ptr = lanes[0].ctr; mp.mem_mask = mem_mask;
     mp.dec_bias = dec_bias; mp.lut = lut_dec; mp.bar_ctr = mega_bar;
+    mp.rs = a.get<float>(3 * 32);
+    mp.dbg_host = pinned_flag + 8;
+    for (int i = 8; i < 16; ++i) pinned_flag[i] = 0;
     if (getenv("MG_MEGA_DBG")) mp.dbg = atoi(getenv("MG_MEGA_DBG"));
     if (getenv("MG_MEGA_GATE")) mp.gate = atoi(getenv("MG_MEGA_GATE"));
     if (getenv("MG_MEGA_INFLIGHT")) mp.max_inflight = std::max(1, std::min(5, atoi(getenv("MG_MEGA_INFLIGHT"))));
@@ -1034,6 +1037,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     // two launches per token: nothing to capture, the host simply runs ahead of the GPU
     pinned_flag[0] = pinned_flag[1] = B;
     bool stop = false;
+    try {
     while (done_steps < total_steps && !stop) {
       const int n = std::min(16, total_steps - done_steps);
       for (int i = 0; i < n; ++i) {
@@ -1045,6 +1049,13 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       if (pinned_flag[0] == 0) stop = true;
       MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? gctr + 3 : lanes[0].ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
       MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
+    }
+    } catch (const Error& e) {
+      if (pinned_flag[8] != 0)  // the fused kernel's watchdog fired: say where
+        throw Error(e.code, std::string(e.what()) + " [decode_step_kernel watchdog: code " + std::to_string(pinned_flag[8]) +
+                                " cta " + std::to_string(pinned_flag[9]) + " thread " + std::to_string(pinned_flag[10]) + " a " +
+                                std::to_string(pinned_flag[11]) + " b " + std::to_string(pinned_flag[12]) + "]");
+      throw;
     }
   } else if (total_steps > 1) {
     // ... then one step per lane is captured and replayed; every kernel reads the step index from device memory
