@@ -105,6 +105,11 @@ int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* i
                       const float* pixel_values, const int64_t* attn_mask, const int64_t* decoder_input_ids, int T,
                       float* logits);
 
+/* Decode-path switches (environment, read when the model is finalised / at every generate call):
+ *   MG_DECODE=chain  use the per-operation kernel chain (CUDA-graph replayed) instead of the fused persistent
+ *                    decode-step kernel, which is the default whenever B <= 32 and max_length <= 512;
+ *   MG_KV24=0        keep the cross K/V in fp32 (kernel chain only). */
+
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);
 
@@ -121,6 +126,12 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
  * planes: 2 = split-bf16 (near-fp32), 1 = plain bf16. swap_out: write c transposed ([N,M] row-major). */
 int mg_op_gemm(void* stream, int M, int N, int K, const float* a, const float* b, float* c, const float* bias,
                const float* residual, int act, int planes, int block_n, int ksplit, int swap_out);
+
+/* kv24, the storage format of the decoder's cross-attention K/V (the tensors the decode loop re-reads once per
+ * generated token; reference: the fp32 cached key/value states of UdopAttention, modeling_udop.py:569-583): fp32
+ * rounded to nearest-even at 24 bits (sign, 8 exponent, 15 mantissa bits) and stored as a 16-bit plane plus an 8-bit
+ * plane. kt, v: (B, H, 64*Mp) fp32 each; out: (2, B, H, 64*Mp) fp32 = decode(encode(kt)), decode(encode(v)). */
+int mg_op_kv24_roundtrip(void* stream, int B, int H, int Mp, const float* kt, const float* v, float* out);
 
 /* HOST-only: T5/UDOP relative-position bucket LUT, lut[n] = bucket of |relative_position| = n without the
  * bidirectional sign offset (transformers/models/udop/modeling_udop.py:466-512). Needs no GPU. */

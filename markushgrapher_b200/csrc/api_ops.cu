@@ -2,7 +2,7 @@
 // kernels through the C ABI with plain device pointers. Declared in include/mg_b200.h.
 #include <string>
 
-#include "mg_internal.h"
+#include "kernels.h"
 #include "mg_b200.h"
 
 namespace mg {
@@ -62,6 +62,18 @@ int mg_op_gemm(void* stream, int M, int N, int K, const float* a, const float* b
   MG_CHECK_CUDA(cudaFreeAsync(al, st));
   MG_CHECK_CUDA(cudaFreeAsync(bh, st));
   MG_CHECK_CUDA(cudaFreeAsync(bl, st));
+  MG_API_END
+}
+
+int mg_op_kv24_roundtrip(void* stream, int B, int H, int Mp, const float* kt, const float* v, float* out) {
+  MG_API_BEGIN
+  using namespace mg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MG_REQUIRE(B > 0 && H > 0 && Mp > 0 && Mp % 8 == 0, "kv24: Mp must be a positive multiple of 8");
+  uint8_t* packed;
+  MG_CHECK_CUDA(cudaMallocAsync(&packed, (size_t)B * H * 384 * Mp, st));
+  launch_kv24_roundtrip(st, kt, v, B, H, Mp, packed, out);
+  MG_CHECK_CUDA(cudaFreeAsync(packed, st));
   MG_API_END
 }
 

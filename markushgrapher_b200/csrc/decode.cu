@@ -367,8 +367,8 @@ void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int
 // =====================================================================================================
 // "kv24" cross K/V: the decode loop re-reads the image's cross K and V of every layer once per generated token,
 // which is the bulk of the step's HBM traffic.  Both are stored with 24 significant bits per element -- fp32
-// rounded to nearest-even at mantissa bit 15, i.e. the same 2^-17 relative precision as the split-bf16 GEMM operands
-// that produced them -- as a 16-bit plane (sign, exponent, 7 mantissa bits = the bf16 truncation) plus an 8-bit
+// rounded to nearest-even to 15 stored mantissa bits (relative error <= 2^-16, the same order as the split-bf16 GEMM
+// operands that produced them) -- as a 16-bit plane (sign, exponent, 7 mantissa bits = the bf16 truncation) plus an 8-bit
 // plane (the next 8 mantissa bits).  3 bytes instead of 4: the dominant kernel moves 25 % fewer bytes.
 // Per (image, head) block of 384*Mp bytes, n = 64*Mp:
 //   [K^T hi: 64 x Mp u16][K^T lo: 64 x Mp u8][V hi: Mp x 64 u16][V lo: Mp x 64 u8]
@@ -402,6 +402,27 @@ void launch_kv24_pack(cudaStream_t st, const float* kt, const float* v, int B, i
   const int64_t n = (int64_t)64 * Mp, n_bh = (int64_t)B * H;
   const int blocks = (int)std::min<int64_t>((n_bh * n / 4 + 255) / 256, 148 * 16);
   kv24_pack_kernel<<<blocks, 256, 0, st>>>(kt, v, n, n_bh, out);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// fp32 -> kv24 block -> fp32 (parity tests of the storage format): x holds n_bh blocks of n = 64*Mp floats, laid out
+// like one layer's cross K^T; `packed` (6*n bytes per block) is scratch.
+__global__ void kv24_unpack_k_kernel(const uint8_t* __restrict__ packed, int64_t n, int64_t n_bh, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_bh * n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bh = i / n, e = i % n;
+    const uint8_t* blk = packed + bh * 6 * n;
+    const uint32_t hi = reinterpret_cast<const uint16_t*>(blk)[e], lo = blk[2 * n + e];
+    const uint32_t hv = reinterpret_cast<const uint16_t*>(blk + 3 * n)[e], lv = blk[5 * n + e];
+    out[i] = __uint_as_float((hi << 16) | (lo << 8));
+    out[n_bh * n + i] = __uint_as_float((hv << 16) | (lv << 8));
+  }
+}
+void launch_kv24_roundtrip(cudaStream_t st, const float* kt, const float* v, int B, int H, int Mp, uint8_t* packed,
+                           float* out) {
+  launch_kv24_pack(st, kt, v, B, H, Mp, packed);
+  const int64_t n = (int64_t)64 * Mp, n_bh = (int64_t)B * H;
+  const int blocks = (int)std::min<int64_t>((n_bh * n + 255) / 256, 148 * 16);
+  kv24_unpack_k_kernel<<<blocks, 256, 0, st>>>(packed, n, n_bh, out);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 

@@ -233,7 +233,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
       // everything streamed through the ring is read exactly once per step: evict-first keeps the small hot data
       // (activations, masks, norm weights, bias tables) resident in L2 underneath a ~9 GB/step stream
       uint64_t pol_stream;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      if (p.dbg & 4)
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
+      else
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
       for (int l = 0; l <= NL; ++l) {
         const MegaLayer& L = s_layers[min(l, NL - 1)];
         const int nph = l < NL ? 8 : 1;

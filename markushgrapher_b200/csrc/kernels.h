@@ -42,6 +42,8 @@ void launch_cross_attn_stream(cudaStream_t st, const float* q, int B, int H, int
                               int Mp, const int* mask, float* ctx);
 // kv24 cross K/V (decode.cu): fp32 rounded to 24 significant bits, stored as a 16-bit + an 8-bit plane
 void launch_kv24_pack(cudaStream_t st, const float* kt, const float* v, int B, int H, int Mp, uint8_t* out);
+void launch_kv24_roundtrip(cudaStream_t st, const float* kt, const float* v, int B, int H, int Mp, uint8_t* packed,
+                           float* out);
 void launch_cross_attn_stream24(cudaStream_t st, const float* q, int B, int H, int D, const uint8_t* kv, int Mp,
                                 const int* mask, float* ctx);
 void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
@@ -121,7 +123,7 @@ struct MegaParams {
   const int* lut;
   float* rs;          // [3][32] RMSNorm row scales published by the qkv / cq / wi phases for their consumers
   unsigned* bar_ctr;  // [2], zero before the first step
-  int gate = 1;          // 1: attention K/V streams wait until the consumers enter their phase
+  int gate = 0;          // 1: attention K/V streams wait until the consumers enter their phase (measured: no gain)
   int* dbg_host = nullptr;  // host-mapped pinned words for the watchdog's diagnostics (may be null)
   int dbg = 0;           // profiling builds (-DMK_FINE) only: 1 = skip the reductions, 2 = skip the TMEM loads
   int max_inflight = 5;  // bulk loads one SM keeps in flight (<= ring stages)

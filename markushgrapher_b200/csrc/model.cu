@@ -454,7 +454,7 @@ void mg_model::finalize(cudaStream_t st) {
   // ---- fused decode step: decoder weights re-tiled as a stream of pre-swizzled 32 KB shared-memory images
   {
     const char* mode = getenv("MG_DECODE");
-    const bool want = mode && std::string(mode) == "mega";  // opt-in until it beats the kernel chain
+    const bool want = !(mode && std::string(mode) == "chain");
     mega_ctas = (want && split2) ? mega_max_ctas() : 0;
     if (mega_ctas > 0) {
       const int NL = c.num_decoder_layers, dff = c.d_ff;
@@ -833,7 +833,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   a.reset();
   // fused persistent decode step (decode_mega.cu) whenever the batch fits one activation tile
   // cross K/V with 24 significant bits (3 bytes / element) unless MG_KV24=0
-  static const bool env_kv24 = !(getenv("MG_KV24") && getenv("MG_KV24")[0] == '0');
+  const bool env_kv24 = !(getenv("MG_KV24") && getenv("MG_KV24")[0] == '0');
   const bool kv24 = env_kv24 && Mp % 8 == 0 && Mp <= 2048;
   const bool use_mega = mega_ctas > 0 && kv24 && B <= 32 && max_length <= 512 && NL <= 24;
   const int Tp = (int)rup(max_length, use_mega ? 32 : 4);
