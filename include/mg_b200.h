@@ -113,6 +113,11 @@ int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* i
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);
 
+/* The decode-step loop of the last greedy mg_generate call alone (encoder and cross-K/V projection excluded), timed
+ * with CUDA events on the launch stream: total milliseconds, steps executed, and whether the fused persistent
+ * decode-step kernel ran (1) or the per-operation kernel chain (0). Host pointers, any may be NULL. */
+int mg_last_decode_loop(mg_model* m, float* loop_ms, int32_t* steps, int32_t* fused);
+
 /* Measurement hook for bench.py: re-launches the decode cross-attention kernel (the dominant, HBM-bound kernel of
  * the path) over the cross-KV buffers of the preceding mg_generate call, every decoder layer in turn (each
  * layer's K/V is larger than L2, so every launch is cache-cold), `reps` times between CUDA events on `stream`.

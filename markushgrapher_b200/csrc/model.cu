@@ -177,6 +177,10 @@ struct mg_model {
   int* mem_mask = nullptr;  // [B, Mp]
   int64_t launches = 0;
   float last_encode_ms = 0.f, last_decode_ms = 0.f;
+  float last_loop_ms = 0.f;   // the decode-step loop alone (cross-KV projection excluded), CUDA events on the stream
+  int last_loop_steps = 0;
+  int last_fused = 0;         // 1 if the last greedy generate used the fused persistent decode-step kernel
+  cudaEvent_t ev_loop[2] = {nullptr, nullptr};
   int64_t last_launches = 0;
   int* pinned_flag = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -212,6 +216,8 @@ struct mg_model {
       if (e) cudaEventDestroy(e);
     if (comm) nccl_api().CommDestroy(comm);
     for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : ev_loop)
       if (e) cudaEventDestroy(e);
   }
 
@@ -482,6 +488,7 @@ void mg_model::finalize(cudaStream_t st) {
   }
   MG_CHECK_CUDA(cudaMallocHost((void**)&pinned_flag, 64));
   for (auto& e : ev) MG_CHECK_CUDA(cudaEventCreate(&e));
+  for (auto& e : ev_loop) MG_CHECK_CUDA(cudaEventCreate(&e));
   MG_CHECK_CUDA(cudaStreamSynchronize(st));
   raw.clear();
   finalized = true;
@@ -1029,6 +1036,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   prof_bn = lanes[0].bn;
   const int total_steps = max_length - 1;
   int done_steps = 0;
+  MG_CHECK_CUDA(cudaEventRecord(ev_loop[0], st));
   // step 0 runs eagerly (lazy one-time initialisation happens outside graph capture) ...
   for (int i = 0; i < nlanes; ++i) one_step(lanes[i]);
   done_steps = 1;
@@ -1102,11 +1110,15 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     MG_CHECK_CUDA(cudaEventRecord(lane_ev[1], aux_stream));
     MG_CHECK_CUDA(cudaStreamWaitEvent(st, lane_ev[1], 0));
   }
+  MG_CHECK_CUDA(cudaEventRecord(ev_loop[1], st));
   if (out_len) {
     launch_out_len(st, ids_dev, B, max_length, std::min(done_steps + 1, max_length), c.eos_token_id, out_len);
     ++launches;
   }
   MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  MG_CHECK_CUDA(cudaEventElapsedTime(&last_loop_ms, ev_loop[0], ev_loop[1]));
+  last_loop_steps = done_steps;
+  last_fused = use_mega ? 1 : 0;
   if (use_mega && mp.prof) {
     std::vector<unsigned long long> h((size_t)mega_ctas * 1024);
     MG_CHECK_CUDA(cudaMemcpy(h.data(), mp.prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1493,6 +1505,15 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
     *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->cur_M * d * (m->prof_kv24 ? 3 : 4) + (int64_t)m->cur_M * 4 +
                                       (int64_t)d * 4 + (int64_t)d * (m->split2 ? 4 : 2));
   if (n_launches) *n_launches = reps * NL;
+  MG_API_END
+}
+
+int mg_last_decode_loop(mg_model* m, float* loop_ms, int32_t* steps, int32_t* fused) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (loop_ms) *loop_ms = m->last_loop_ms;
+  if (steps) *steps = m->last_loop_steps;
+  if (fused) *fused = m->last_fused;
   MG_API_END
 }
 

@@ -95,6 +95,7 @@ class MGEngine:
         L.mg_generate_host.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] +
                                        [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3)
         L.mg_last_stats.argtypes = [ctypes.c_void_p] * 4
+        L.mg_last_decode_loop.argtypes = [ctypes.c_void_p] * 4
         L.mg_destroy.argtypes = [ctypes.c_void_p]
         L.mg_destroy.restype = None
         self.n_patches = (cfg.image_size // cfg.patch_size) ** 2
@@ -231,6 +232,12 @@ class MGEngine:
             _lib.check(L.mg_profile_cross_attn(self._h, _lib.cur_stream(), reps, ctypes.addressof(ms),
                                                ctypes.addressof(by), ctypes.addressof(n)), "mg_profile_cross_attn")
         return {"ms_per_launch": ms.value, "bytes_per_launch": by.value, "launches": n.value}
+
+    def last_decode_loop(self):
+        ms, n, f = ctypes.c_float(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.check(_lib.lib().mg_last_decode_loop(self._h, ctypes.addressof(ms), ctypes.addressof(n),
+                                                  ctypes.addressof(f)), "mg_last_decode_loop")
+        return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value)}
 
     def last_stats(self):
         e, d, k = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int64(0)

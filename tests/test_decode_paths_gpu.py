@@ -1,6 +1,7 @@
 """GPU: the two decode paths (fused persistent decode-step kernel / per-operation kernel chain) and the kv24 storage
 format of the cross K/V.  Properties that do not need the oracle are checked at the full model size and batch 32,
 where every CTA of the fused kernel carries four concurrent self-attention items and four cross-attention items."""
+import ctypes
 import os
 
 import numpy as np
@@ -47,6 +48,8 @@ def test_kv24_roundtrip_bit_exact_and_idempotent():
     v[0, 0, :8] = torch.tensor([0.0, -0.0, 1.0, -1.0, 2.0 ** -126, 3.0e38, 1.0 + 2.0 ** -16, 1.0 + 2.0 ** -15])
     out = torch.empty(2, B, H, 64 * Mp, device="cuda")
     ktd, vd = kt.cuda(), v.cuda()
+    _lib.lib().mg_op_kv24_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     rc = _lib.lib().mg_op_kv24_roundtrip(_lib.cur_stream(), B, H, Mp, _lib.ptr(ktd), _lib.ptr(vd), _lib.ptr(out))
     _lib.check(rc, "mg_op_kv24_roundtrip")
     torch.cuda.synchronize()
@@ -96,6 +99,7 @@ def test_full_size_batch32_paths_agree():
             ids = eng.generate(**inp, max_length=200, trim=False)
             ids_s, lg = eng.generate(**{k: v[:4] for k, v in inp.items()}, max_length=6, return_logits=True)
             launches = eng.last_stats()["kernels"]
+            assert eng.last_decode_loop()["fused"] == (tag == "fused")
             eng.close()
         res[tag] = (ids.cpu(), lg.cpu(), launches)
         torch.cuda.empty_cache()
