@@ -138,6 +138,19 @@ int mg_op_gemm(void* stream, int M, int N, int K, const float* a, const float* b
  * plane. kt, v: (B, H, 64*Mp) fp32 each; out: (2, B, H, 64*Mp) fp32 = decode(encode(kt)), decode(encode(v)). */
 int mg_op_kv24_roundtrip(void* stream, int B, int H, int Mp, const float* kt, const float* v, float* out);
 
+/* ---- GPU input packing: the step in front of the path --------------------------------------
+ * src: B page images, uint8 RGB, (B, Hin, Win, 3) on the device.  out: pixel_values (B, 3, Hout, Wout) fp32 =
+ *   page_image.resize((Wout, Hout), resample=Image.LANCZOS | BILINEAR)      reference core/datasets/mdu_dataset.py:118
+ *   -> image processor: x * 1/255, (x - mean) / std                           reference utils/common.py:34-42
+ * The resize restates Pillow's two-pass fixed-point resampler exactly (bit-identical to PIL, tests/test_pack_*.py);
+ * filter: 0 = BILINEAR, 1 = LANCZOS.  mean / std: 3 host floats each.  Asynchronous on `stream`. */
+int mg_pack_pixels(void* stream, int B, int Hin, int Win, const uint8_t* src, int Hout, int Wout, int filter,
+                   const float* mean3_host, const float* std3_host, float* out);
+/* HOST-only: Pillow's resampling coefficient table for one axis (precompute_coeffs + normalize_coeffs_8bpc):
+ * bounds_host (2*out_size: first source index, count), kk_host (out_size * ksize 22-bit fixed-point weights). */
+int mg_resample_coeffs(int in_size, int out_size, int filter, int32_t* ksize_out, int32_t* bounds_host, int32_t* kk_host,
+                       int kk_capacity);
+
 /* HOST-only: T5/UDOP relative-position bucket LUT, lut[n] = bucket of |relative_position| = n without the
  * bidirectional sign offset (transformers/models/udop/modeling_udop.py:466-512). Needs no GPU. */
 int mg_rel_bucket_lut(int bidirectional, int num_buckets, int max_distance, int n_entries, int32_t* lut_host);

@@ -77,4 +77,33 @@ int mg_op_kv24_roundtrip(void* stream, int B, int H, int Mp, const float* kt, co
   MG_API_END
 }
 
+int mg_pack_pixels(void* stream, int B, int Hin, int Win, const uint8_t* src, int Hout, int Wout, int filter,
+                   const float* mean3_host, const float* std3_host, float* out) {
+  MG_API_BEGIN
+  using namespace mg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MG_REQUIRE(src && out && mean3_host && std3_host, "mg_pack_pixels: null pointer");
+  uint8_t* tmp = nullptr;
+  if (Win != Wout) MG_CHECK_CUDA(cudaMallocAsync(&tmp, (size_t)B * Hin * Wout * 3, st));
+  launch_pack_pixels(st, B, Hin, Win, src, Hout, Wout, filter, mean3_host, std3_host, tmp, out);
+  if (tmp) MG_CHECK_CUDA(cudaFreeAsync(tmp, st));
+  MG_API_END
+}
+
+int mg_resample_coeffs(int in_size, int out_size, int filter, int32_t* ksize_out, int32_t* bounds_host, int32_t* kk_host,
+                       int kk_capacity) {
+  MG_API_BEGIN
+  using namespace mg;
+  std::vector<int> b, k;
+  const int ksize = resample_coeffs(in_size, out_size, filter, b, k);
+  if (ksize_out) *ksize_out = ksize;
+  if (bounds_host)
+    for (size_t i = 0; i < b.size(); ++i) bounds_host[i] = b[i];
+  if (kk_host) {
+    MG_REQUIRE((size_t)kk_capacity >= k.size(), "mg_resample_coeffs: kk_capacity too small (need out_size * ksize)");
+    for (size_t i = 0; i < k.size(); ++i) kk_host[i] = k[i];
+  }
+  MG_API_END
+}
+
 }  // extern "C"

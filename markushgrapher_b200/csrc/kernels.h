@@ -1,5 +1,7 @@
 // Launch wrappers of all non-GEMM kernels (definitions in ops.cu / swin.cu / decode.cu).
 #pragma once
+#include <vector>
+
 #include "mg_internal.h"
 
 namespace mg {
@@ -90,6 +92,11 @@ void launch_beam_finalize(cudaStream_t st, const BeamState& s, int pad, int64_t*
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
                       bool store, float* amax_val = nullptr, int* amax_idx = nullptr);
+
+// ---- pack.cu: GPU input packing (Pillow-exact resize + image-processor normalisation)
+int resample_coeffs(int in_size, int out_size, int filter, std::vector<int>& bounds, std::vector<int>& kk);
+void launch_pack_pixels(cudaStream_t st, int B, int Hin, int Win, const uint8_t* src, int Hout, int Wout, int filter,
+                        const float* mean3, const float* std3, uint8_t* tmp, float* out);
 
 // ---- decode_mega.cu: the fused persistent decode step (one cooperative kernel per generated token)
 struct MegaLin {           // a linear layer as a stream of pre-swizzled 32 KB (tile, k-block) weight tiles
