@@ -151,6 +151,23 @@ int mg_pack_pixels(void* stream, int B, int Hin, int Win, const uint8_t* src, in
 int mg_resample_coeffs(int in_size, int out_size, int filter, int32_t* ksize_out, int32_t* bounds_host, int32_t* kk_host,
                        int kk_capacity);
 
+/* ---- batched detokeniser: the step behind the path --------------------------------------
+ * ids (B, T) i64 on the device -> the strings of MarkushTokenizer.decode_plus_decode_other_tokens, reference
+ * markushgrapher/core/common/markush_tokenizer.py:615-670.  The table is built on the host from the tokenizer's
+ * id -> piece list and the reference's <other_N> vocabulary (markushgrapher_b200/detok.py evaluates every string
+ * predicate of the reference once per vocabulary entry): text = UTF-8 bytes emitted for an id (space marker
+ * stripped; "<mapped> " for a known <other_N>), text_off (vocab+1) their offsets, flags (vocab): 1 contains <i>,
+ * 2 equals </i>, 4 contains </i>, 8 location token, 16 <other_*> token, 32 "the previous token gets a space".
+ * mg_detok_measure: row lengths (lens (B) i32 or NULL = T tokens per row) -> row_off_host (B+1) byte offsets
+ * (synchronises); mg_detok_write: the bytes, rows back to back, into out (row_off_host[B] bytes, device). */
+typedef struct mg_detok mg_detok;
+int mg_detok_create(int vocab, const uint8_t* text_host, const int32_t* text_off_host, const uint8_t* flags_host,
+                    mg_detok** out);
+void mg_detok_destroy(mg_detok* d);
+int mg_detok_measure(mg_detok* d, void* stream, int B, int T, const int64_t* ids, const int32_t* lens,
+                     int64_t* row_off_host);
+int mg_detok_write(mg_detok* d, void* stream, int B, int T, const int64_t* ids, uint8_t* out);
+
 /* HOST-only: T5/UDOP relative-position bucket LUT, lut[n] = bucket of |relative_position| = n without the
  * bidirectional sign offset (transformers/models/udop/modeling_udop.py:466-512). Needs no GPU. */
 int mg_rel_bucket_lut(int bidirectional, int num_buckets, int max_distance, int n_entries, int32_t* lut_host);

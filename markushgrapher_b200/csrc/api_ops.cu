@@ -106,4 +106,71 @@ int mg_resample_coeffs(int in_size, int out_size, int filter, int32_t* ksize_out
   MG_API_END
 }
 
+// ---- batched detokeniser ------------------------------------------------------------------------------------
+struct mg_detok {
+  int vocab = 0;
+  int* text_off = nullptr;
+  uint8_t* text = nullptr;
+  uint8_t* flags = nullptr;
+  // scratch of the last measure call
+  int *tok_off = nullptr, *tok_len = nullptr;
+  int64_t *row_len = nullptr, *row_off = nullptr;
+  int cap_B = 0, cap_T = 0;
+};
+
+int mg_detok_create(int vocab, const uint8_t* text_host, const int32_t* text_off_host, const uint8_t* flags_host,
+                    mg_detok** out) {
+  MG_API_BEGIN
+  using namespace mg;
+  MG_REQUIRE(vocab > 0 && text_off_host && flags_host && out, "mg_detok_create: bad arguments");
+  mg_detok* d = new mg_detok();
+  d->vocab = vocab;
+  const size_t nbytes = (size_t)text_off_host[vocab];
+  MG_CHECK_CUDA(cudaMalloc((void**)&d->text_off, sizeof(int) * (vocab + 1)));
+  MG_CHECK_CUDA(cudaMalloc((void**)&d->text, std::max<size_t>(nbytes, 16)));
+  MG_CHECK_CUDA(cudaMalloc((void**)&d->flags, vocab));
+  MG_CHECK_CUDA(cudaMemcpy(d->text_off, text_off_host, sizeof(int) * (vocab + 1), cudaMemcpyHostToDevice));
+  if (nbytes) MG_CHECK_CUDA(cudaMemcpy(d->text, text_host, nbytes, cudaMemcpyHostToDevice));
+  MG_CHECK_CUDA(cudaMemcpy(d->flags, flags_host, vocab, cudaMemcpyHostToDevice));
+  *out = d;
+  MG_API_END
+}
+
+void mg_detok_destroy(mg_detok* d) {
+  if (!d) return;
+  cudaFree(d->text_off); cudaFree(d->text); cudaFree(d->flags);
+  cudaFree(d->tok_off); cudaFree(d->tok_len); cudaFree(d->row_len); cudaFree(d->row_off);
+  delete d;
+}
+
+int mg_detok_measure(mg_detok* d, void* stream, int B, int T, const int64_t* ids, const int32_t* lens,
+                     int64_t* row_off_host) {
+  MG_API_BEGIN
+  using namespace mg;
+  MG_REQUIRE(d && ids && B > 0 && T > 0 && row_off_host, "mg_detok_measure: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B > d->cap_B || T > d->cap_T) {
+    cudaFree(d->tok_off); cudaFree(d->tok_len); cudaFree(d->row_len); cudaFree(d->row_off);
+    d->cap_B = std::max(B, d->cap_B);
+    d->cap_T = std::max(T, d->cap_T);
+    MG_CHECK_CUDA(cudaMalloc((void**)&d->tok_off, sizeof(int) * (size_t)d->cap_B * d->cap_T));
+    MG_CHECK_CUDA(cudaMalloc((void**)&d->tok_len, sizeof(int) * (size_t)d->cap_B * d->cap_T));
+    MG_CHECK_CUDA(cudaMalloc((void**)&d->row_len, sizeof(int64_t) * d->cap_B));
+    MG_CHECK_CUDA(cudaMalloc((void**)&d->row_off, sizeof(int64_t) * (d->cap_B + 1)));
+  }
+  launch_detok_measure(st, ids, B, T, lens, d->text_off, d->flags, d->vocab, d->tok_off, d->tok_len, d->row_len, d->row_off);
+  MG_CHECK_CUDA(cudaMemcpyAsync(row_off_host, d->row_off, sizeof(int64_t) * (B + 1), cudaMemcpyDeviceToHost, st));
+  MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  MG_API_END
+}
+
+int mg_detok_write(mg_detok* d, void* stream, int B, int T, const int64_t* ids, uint8_t* out) {
+  MG_API_BEGIN
+  using namespace mg;
+  MG_REQUIRE(d && ids && out && B > 0 && T > 0 && B <= d->cap_B && T <= d->cap_T, "mg_detok_write: call mg_detok_measure first");
+  launch_detok_write(static_cast<cudaStream_t>(stream), ids, B, T, d->text_off, d->text, d->vocab, d->tok_off, d->tok_len,
+                     d->row_off, out);
+  MG_API_END
+}
+
 }  // extern "C"

@@ -98,6 +98,12 @@ int resample_coeffs(int in_size, int out_size, int filter, std::vector<int>& bou
 void launch_pack_pixels(cudaStream_t st, int B, int Hin, int Win, const uint8_t* src, int Hout, int Wout, int filter,
                         const float* mean3, const float* std3, uint8_t* tmp, float* out);
 
+// ---- detok.cu: batched detokeniser (ids -> bytes; flags / text table built on the host)
+void launch_detok_measure(cudaStream_t st, const int64_t* ids, int B, int T, const int* lens, const int* text_off,
+                          const uint8_t* flags, int vocab, int* tok_off, int* tok_len, int64_t* row_len, int64_t* row_off);
+void launch_detok_write(cudaStream_t st, const int64_t* ids, int B, int T, const int* text_off, const uint8_t* text,
+                        int vocab, const int* tok_off, const int* tok_len, const int64_t* row_off, uint8_t* out);
+
 // ---- decode_mega.cu: the fused persistent decode step (one cooperative kernel per generated token)
 struct MegaLin {           // a linear layer as a stream of pre-swizzled 32 KB (tile, k-block) weight tiles
   const uint8_t* w = nullptr;  // [tiles][num_kb][hi 16 KB | lo 16 KB]
