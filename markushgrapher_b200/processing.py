@@ -1,6 +1,9 @@
 """Host-side mirrors of the fork's image processor / tokenizer / processor classes (reference begin.py:105-111,
-utils/common.py:34-42). CPU-side input packing only — the tensors they emit are the hot path's input contract:
-input_ids (1,Lt) i64, bbox (1,Lt,4) f32 in [0,1], attention_mask (1,Lt), pixel_values (1,3,512,512) f32."""
+utils/common.py:34-42) and of the OCR-cell packing in front of them (core/common/data_preprocessing.py:24-104,
+core/datasets/task_collator.py:28-107). The tensors they emit are the hot path's input contract:
+input_ids (1,Lt) i64, bbox (1,Lt,4) f32 in [0,1], attention_mask (1,Lt), pixel_values (1,3,512,512) f32.
+String / sub-word work stays on the host (it is sentencepiece-bound); the pixel side has a device implementation in
+packing.py."""
 from __future__ import annotations
 
 import os
@@ -8,6 +11,61 @@ from typing import List, Optional
 
 import numpy as np
 import torch
+
+
+# ------------------------------------------------------------------------------------------------ OCR cells
+def split_bounding_box_for_words(sentence: str, bounding_box, tokenizer):
+    """One OCR cell -> its sentencepiece pieces and one box per piece: the cell's width is shared out in proportion
+    to a 12-px-per-character estimate, left to right (reference data_preprocessing.py:16-48).  Arithmetic is in
+    Python floats (doubles) in the reference's order -- fraction first, then the running left edge -- so the boxes
+    are bit-identical (tests/test_cells_cpu.py replays golden vectors from the reference's own function)."""
+    pieces = tokenizer.tokenize(sentence)
+    widths = np.array([12 * (1 if p == "▁" else sum(ch != "▁" for ch in p)) for p in pieces], dtype=np.float64)
+    x_min, y_min, x_max, y_max = bounding_box
+    if len(pieces) == 0:
+        return pieces, []
+    adjusted = (x_max - x_min) * (widths / float(widths.sum()))
+    edges = np.cumsum(np.concatenate(([x_min], adjusted)))          # sequential: left_{i+1} = left_i + adjusted_i
+    return pieces, [(float(edges[i]), y_min, float(edges[i] + adjusted[i]), y_max) for i in range(len(pieces))]
+
+
+def prepare_cells_to_text(cells, tokenizer, w, h, normalize_bbox: bool, max_sequence_length: int = 512):
+    """OCR cells [{"text", "bbox" in [0,1]}] -> (words, boxes, token count): the in-memory hand-off from ChemicalOCR
+    (reference ocr/chemical_ocr.py:396-478 writes exactly these cells to disk) to the processor, reference
+    data_preprocessing.py:59-104.  normalize_bbox=False is the pre-2025 0..500 integer box format."""
+    words, boxes, n_tok = [], [], 0
+    for cell in cells:
+        text = cell["text"]
+        if text.isspace():
+            continue
+        bx = cell["bbox"]
+        pieces, piece_boxes = split_bounding_box_for_words(text, [bx[0] * w, bx[1] * h, bx[2] * w, bx[3] * h], tokenizer)
+        for piece, box in zip(pieces, piece_boxes):
+            if piece.isspace():
+                continue
+            if not normalize_bbox:
+                box = (int((box[0] / w) * 500), int((box[1] / h) * 500), int((box[2] / w) * 500), int((box[3] / h) * 500))
+            if max(box) > 500:
+                continue
+            word = str(piece).strip()
+            words.append(word)
+            boxes.append(box)
+            n_tok += len(tokenizer.tokenize(word))
+            if n_tok >= max_sequence_length - 15:
+                break
+        if n_tok >= max_sequence_length:
+            break
+    return words, boxes, n_tok
+
+
+def collate_cells(image, cells, tokenizer, question: str, normalize_bbox: bool = True):
+    """(page image, OCR cells, question) -> (image, instruction, words, boxes) as TaskCollator.collate returns them
+    (reference core/datasets/task_collator.py:28-107; the label half is training-only)."""
+    w, h = image.size
+    words, boxes, _ = prepare_cells_to_text(cells, tokenizer, w, h, normalize_bbox)
+    if normalize_bbox:
+        boxes = [[b[0] / w, b[1] / h, b[2] / w, b[3] / h] for b in boxes]
+    return image, f"Question Answering. {question}", words, boxes
 
 
 class MarkushgrapherImageProcessor:
@@ -118,6 +176,13 @@ class MarkushgrapherProcessor:
         self.image_processor = image_processor
         self.tokenizer = tokenizer
         self.sep_box = list(sep_box)
+
+    def from_cells(self, image, cells, question: str = "What markush structure is in the image?",
+                   normalize_bbox: bool = True):
+        """ChemicalOCR cells straight to model inputs (no dataset round trip through the disk): collate + __call__,
+        the two steps of reference utils/common.py:14-42"""
+        image, instruction, words, boxes = collate_cells(image, cells, self.tokenizer, question, normalize_bbox)
+        return self(images=image.convert("RGB"), text=[instruction], text_pair=[words], boxes=[boxes])
 
     def __call__(self, images=None, text=None, text_pair=None, boxes=None, return_tensors="pt", padding=False,
                  truncation=False, max_length: Optional[int] = None, **kw):
