@@ -324,7 +324,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
     }
   } else if (warp == 1) {
     // =============================================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow and one elected lane issues: with a divergent
+    // `if (lane == 0)` the compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in an
+    // ELECT / R2UR loop (~17 instructions per MMA on the critical path of every linear).
+    {
       RingPos r;
       uint32_t n_item = 0;
       constexpr uint32_t idesc = make_idesc_bf16(128, MK_R);
@@ -363,16 +366,22 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               const uint64_t da_hi = make_sw128_kmajor_desc(sa), da_lo = make_sw128_kmajor_desc(sa + 16384);
               const uint64_t db_hi = make_sw128_kmajor_desc(sa + MK_XOFF);
               const uint64_t db_lo = make_sw128_kmajor_desc(sa + MK_XOFF + MK_XPLANE);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) { umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, acc); acc = 1; }
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
-              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty + 8 * r.s) : "memory");
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty + 8 * r.s) : "memory");
+              }
+              __syncwarp();
+              acc = 1;
               r.adv();
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull) : "memory");
+            if (elect_one())
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull) : "memory");
+            __syncwarp();
             MK_STAMP(fm, 3);
             ++n_item;
           }

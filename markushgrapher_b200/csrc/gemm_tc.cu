@@ -119,8 +119,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         }
       }
     } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      // The whole warp runs the (warp-uniform) loop and one elected lane issues.  Under a divergent `if (lane == 0)`
+      // the compiler cannot keep the descriptors in uniform registers and wraps every tcgen05.mma in an
+      // ELECT / R2UR loop (~17 instructions, about as long as a 128x128x16 MMA runs): the issue loop, not the
+      // tensor pipe, paced the kernel.  Now: ~2 uniform-datapath instructions per MMA.
+      {
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
         int s = 0;
         uint32_t ph = 0;
@@ -133,28 +137,30 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const uint64_t da_lo = make_sw128_kmajor_desc(sa + A_BYTES);
           const uint64_t db_hi = make_sw128_kmajor_desc(sa + 2 * A_BYTES);
           const uint64_t db_lo = make_sw128_kmajor_desc(sa + 2 * A_BYTES + C::B_BYTES);
-          if (p.nplanes == 2) {
-            // small cross terms first, the dominant hi*hi product last
+          if (elect_one()) {
+            if (p.nplanes == 2) {
+              // small cross terms first, the dominant hi*hi product last
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, acc);
-              acc = 1;
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
             }
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+            umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
           }
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, acc);
-            acc = 1;
-          }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
+          acc = 1;
           if (++s == C::STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(tmem_full_bar);  // accumulator complete
+        if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
     } else {
       // ------------------------------------------------------------------ epilogue (warps 2..5)
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform loop, one elected lane issues (see gemm_tc_kernel)
       constexpr uint32_t idesc = make_idesc_bf16(BM, R);
       int s = 0;
       uint32_t ph = 0, acc = 0;
@@ -467,18 +473,26 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
         const uint64_t da_hi = make_sw128_kmajor_desc(sa), da_lo = make_sw128_kmajor_desc(sa + A_BYTES);
         const uint64_t db_hi = make_sw128_kmajor_desc(sa + 2 * A_BYTES);
         const uint64_t db_lo = make_sw128_kmajor_desc(sa + 2 * A_BYTES + X_BYTES);
-        if (p.nplanes == 2) {
+        if (elect_one()) {
+          if (p.nplanes == 2) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) { umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, acc); acc = 1; }
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) { umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, acc); acc = 1; }
-        umma_commit(&empty_bar[s]);
+        __syncwarp();
+        acc = 1;
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
   } else if (warp >= 6) {
     // ---------------------------------------------------------------- statistic warps (6..9, 128 threads)
