@@ -21,7 +21,8 @@ namespace mg {
 struct alignas(64) GemmParams {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int M, N, K;
-  int nb1;           // blockIdx.z = ks + ksplit * (b1 + nb1 * b2)
+  int nx, ny, nz;    // tile grid: n tiles, m tiles, ksplit * nb1 * nb2
+  int nb1;           // z = ks + ksplit * (b1 + nb1 * b2)
   int ksplit, kb_per_split, num_kb;
   int a_use1, a_use2, b_use1, b_use2;
   int nplanes;       // 2 = hi+lo (3 products), 1 = hi only
@@ -49,26 +50,22 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  // Persistent: one CTA per SM walks the tile list (tile = blockIdx.x, += gridDim.x).  The shared-memory ring and its
+  // barrier phases run on across tiles, and the fp32 accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so the
+  // epilogue of tile i (TMEM -> registers -> global) overlaps the MMAs of tile i+1 and the per-tile prologue
+  // (barrier init, TMEM allocation, tensor-map prefetch) is paid once per SM instead of once per tile.
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], 128 epilogue threads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int ks = blockIdx.z % p.ksplit;
-  const int zb = blockIdx.z / p.ksplit;
-  const int b1 = zb % p.nb1;
-  const int b2 = zb / p.nb1;
-  const int kb0 = ks * p.kb_per_split;
-  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-  const bool has_work = kb0 < kb1;
+  const int total_tiles = p.nx * p.ny * p.nz;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.ta_hi);
@@ -81,40 +78,56 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base0 = *tmem_slot;
 
-  if (has_work) {
+  // tile id -> (n tile, m tile, k-split / batch indices); identical in all three roles
+#define MG_TILE_DECODE(t)                                        \
+  const int tx_ = (t) % p.nx, ty_ = ((t) / p.nx) % p.ny, tz_ = (t) / (p.nx * p.ny); \
+  const int n0 = tx_ * BN, m0 = ty_ * BM;                      \
+  const int ks = tz_ % p.ksplit, zb = tz_ / p.ksplit;          \
+  const int b1 = zb % p.nb1, b2 = zb / p.nb1;                  \
+  const int kb0 = ks * p.kb_per_split;                         \
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+
+  {
+  {
     if (warp == 0) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
-        const int a1 = p.a_use1 ? b1 : 0, a2 = p.a_use2 ? b2 : 0;
-        const int c1 = p.b_use1 ? b1 : 0, c2 = p.b_use2 ? b2 : 0;
         const uint32_t tx = (p.nplanes == 2) ? C::STAGE_BYTES : (A_BYTES + C::B_BYTES);
         int s = 0;
         uint32_t ph = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* st = smem + s * C::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], tx);
-          tma_load_4d(st, &p.ta_hi, &full_bar[s], kb * BK, m0, a1, a2);
-          tma_load_4d(st + 2 * A_BYTES, &p.tb_hi, &full_bar[s], kb * BK, n0, c1, c2);
-          if (p.nplanes == 2) {
-            tma_load_4d(st + A_BYTES, &p.ta_lo, &full_bar[s], kb * BK, m0, a1, a2);
-            tma_load_4d(st + 2 * A_BYTES + C::B_BYTES, &p.tb_lo, &full_bar[s], kb * BK, n0, c1, c2);
-          }
-          if (++s == C::STAGES) {
-            s = 0;
-            ph ^= 1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          MG_TILE_DECODE(tile)
+          const int a1 = p.a_use1 ? b1 : 0, a2 = p.a_use2 ? b2 : 0;
+          const int c1 = p.b_use1 ? b1 : 0, c2 = p.b_use2 ? b2 : 0;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* st = smem + s * C::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], tx);
+            tma_load_4d(st, &p.ta_hi, &full_bar[s], kb * BK, m0, a1, a2);
+            tma_load_4d(st + 2 * A_BYTES, &p.tb_hi, &full_bar[s], kb * BK, n0, c1, c2);
+            if (p.nplanes == 2) {
+              tma_load_4d(st + A_BYTES, &p.ta_lo, &full_bar[s], kb * BK, m0, a1, a2);
+              tma_load_4d(st + 2 * A_BYTES + C::B_BYTES, &p.tb_lo, &full_bar[s], kb * BK, n0, c1, c2);
+            }
+            if (++s == C::STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
       }
@@ -128,44 +141,59 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
         int s = 0;
         uint32_t ph = 0;
-        uint32_t acc = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+          MG_TILE_DECODE(tile)
+          (void)n0; (void)m0; (void)b1; (void)b2;
+          const int ab = it & 1;  // accumulator buffer
+          mbar_wait(&tmem_empty_bar[ab], ((uint32_t)(it >> 1) & 1u) ^ 1u);  // its previous tile has been read out
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-          const uint64_t da_hi = make_sw128_kmajor_desc(sa);
-          const uint64_t da_lo = make_sw128_kmajor_desc(sa + A_BYTES);
-          const uint64_t db_hi = make_sw128_kmajor_desc(sa + 2 * A_BYTES);
-          const uint64_t db_lo = make_sw128_kmajor_desc(sa + 2 * A_BYTES + C::B_BYTES);
-          if (elect_one()) {
-            if (p.nplanes == 2) {
-              // small cross terms first, the dominant hi*hi product last
+          const uint32_t tmem_acc = tmem_base0 + (uint32_t)(ab * BN);
+          uint32_t acc = 0;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint64_t da_hi = make_sw128_kmajor_desc(sa);
+            const uint64_t da_lo = make_sw128_kmajor_desc(sa + A_BYTES);
+            const uint64_t db_hi = make_sw128_kmajor_desc(sa + 2 * A_BYTES);
+            const uint64_t db_lo = make_sw128_kmajor_desc(sa + 2 * A_BYTES + C::B_BYTES);
+            if (elect_one()) {
+              if (p.nplanes == 2) {
+                // small cross terms first, the dominant hi*hi product last
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_lo + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, da_lo + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, da_hi + 2 * k, db_lo + 2 * k, idesc, 1);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
-            } else {
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, da_hi + 2 * k, db_hi + 2 * k, idesc, 1);
+              } else {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, da_hi + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, da_hi + 2 * k, db_hi + 2 * k, idesc, k == 0 ? acc : 1u);
+              }
+              umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
             }
-            umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+            __syncwarp();
+            acc = 1;
+            if (++s == C::STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
           }
+          if (elect_one()) umma_commit(&tmem_full_bar[ab]);  // accumulator complete
           __syncwarp();
-          acc = 1;
-          if (++s == C::STAGES) {
-            s = 0;
-            ph ^= 1;
-          }
         }
-        if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
-        __syncwarp();
       }
     } else {
       // ------------------------------------------------------------------ epilogue (warps 2..5)
       const GemmEpilogue& ep = p.ep;
-      mbar_wait(tmem_full_bar, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      MG_TILE_DECODE(tile)
+      (void)kb0; (void)kb1;
+      const int ab = it & 1;
+      const uint32_t tmem_base = tmem_base0 + (uint32_t)(ab * BN);
+      mbar_wait(&tmem_full_bar[ab], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const int q = warp & 3;  // TMEM lane quadrant this warp may access
       const int m = m0 + q * 32 + lane;
@@ -266,12 +294,18 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           }
         }
       }
+      // every tcgen05.ld of this tile has completed (wait::ld above): hand the accumulator back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[ab]);
+      }
     }
   }
+  }
+#undef MG_TILE_DECODE
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base0, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -362,8 +396,18 @@ void launch_gemm(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, in
              ((reinterpret_cast<uintptr_t>(optr) & 15) == 0) &&
              (!ep.out_lo || (reinterpret_cast<uintptr_t>(ep.out_lo) & 15) == 0) &&
              (!ep.residual || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
-  dim3 grid((N + block_n - 1) / block_n, (M + BM - 1) / BM, ksplit * nb1 * nb2);
-  MG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "GEMM grid too large");
+  p.nx = (N + block_n - 1) / block_n;
+  p.ny = (M + BM - 1) / BM;
+  p.nz = ksplit * nb1 * nb2;
+  const int64_t tiles = (int64_t)p.nx * p.ny * p.nz;
+  MG_REQUIRE(tiles < (int64_t)1 << 30, "GEMM tile count too large");
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    MG_CHECK_CUDA(cudaGetDevice(&dev));
+    MG_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid((unsigned)std::min<int64_t>(tiles, n_sm));  // persistent: one CTA per SM walks the tile list
   if (block_n == 128)
     launch_bn<128>(st, p, grid);
   else if (block_n == 64)
