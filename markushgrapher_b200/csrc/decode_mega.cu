@@ -221,6 +221,23 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
   const int my_attn = g < Ga ? items_of_cta(n_attn, g, Ga) : 0;
   const int attn_first = g < Ga ? g : n_attn;
   const int Tb = p.Tp >> 5;  // 32-key blocks per (image, head) of the self K cache
+  // Cross-attention is balanced by BYTES over all CTAs: an item's K pass and V pass stream equal amounts, so the
+  // 2 * n_attn half-works  K0 V0 K1 V1 ...  are cut into G equal ranges.  A range that ends with a K pass does it
+  // FIRST and publishes the unnormalised probabilities (Mp floats + their sum) through global memory; the next CTA,
+  // whose range starts with that item's V pass, does it LAST -- so the one cross-CTA dependency never waits.
+  const int xh_total = 2 * n_attn, xh_per = (xh_total + G - 1) / G;
+  const int xh_lo = min(g * xh_per, xh_total), xh_hi = min(xh_lo + xh_per, xh_total);
+  const int x_lone_k = (xh_hi > xh_lo && ((xh_hi - 1) & 1) == 0) ? 1 : 0;  // range ends with a K pass
+  const int x_lone_v = (xh_hi > xh_lo && (xh_lo & 1) == 1) ? 1 : 0;        // range starts with a V pass
+  const int x_first = (xh_lo + 1) >> 1;                                     // whole items [x_first, x_first + x_whole)
+  const int x_whole = max(((xh_hi - x_lone_k) >> 1) - x_first, 0);
+  const int x_entries = x_lone_k + x_whole + x_lone_v;
+  // entry e of this CTA's cross schedule -> (item, passes: 1 = K, 2 = V, 3 = both)
+  auto cross_entry = [&](int e, int& item, int& passes) {
+    if (x_lone_k && e == 0) { item = (xh_hi - 1) >> 1; passes = 1; }
+    else if (e - x_lone_k < x_whole) { item = x_first + e - x_lone_k; passes = 3; }
+    else { item = xh_lo >> 1; passes = 2; }
+  };
 
   if (warp == 0) {
     // =============================================================================================== producer
@@ -279,9 +296,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // chunks are interleaved (chunk c of every item of the bundle, then chunk c+1, ...); elsewhere bundle = 1
           const int stride = attn ? Ga : G;
           const int bundle = (attn && ph == 1) ? MK_SELF_NG : 1;
-          for (int it0 = attn ? attn_first : g; it0 < n_items; it0 += stride * bundle) {
+          const bool is_cross = attn && ph == 4;
+          for (int e = 0, it0 = attn ? attn_first : g; is_cross ? e < x_entries : it0 < n_items; ++e, it0 += stride * bundle) {
+            int passes = 3;
+            if (is_cross) cross_entry(e, it0, passes);
             for (int sidx = 0; sidx < 2; ++sidx) {
               if (sidx && !base1) break;
+              if (!((passes >> sidx) & 1)) continue;
               const uint32_t chunk = sidx ? chunk1 : chunk0;
               const int minor0 = it0 % div;
               const uint32_t tot = sidx ? tot1 : (attn ? tot0 : (uint32_t)min(upi, units - minor0 * upi) * MK_WTILE);
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
         const int nph = l < NL ? 8 : 1;
         for (int ph = 0; ph < nph; ++ph) {
           if (l < NL && ph == 1) { r.adv_n(my_attn * (self_nkc + self_nvc)); continue; }
-          if (l < NL && ph == 4) { r.adv_n(my_attn * (cross_nkc + cross_nvc)); continue; }
+          if (l < NL && ph == 4) { r.adv_n((x_whole + x_lone_k) * cross_nkc + (x_whole + x_lone_v) * cross_nvc); continue; }
           const MegaLin& W = l < NL ? L.lin[mega_lin_of_phase(ph)] : p.lm_head;
           const int items = W.tiles * W.ksplit;
 #ifdef MK_FINE
@@ -560,59 +581,92 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // ---------------------------------------------------------------------------------- cross-attention
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
           // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = pair of adjacent keys.
-          for (int it = attn_first; it < n_attn; it += Ga) {
+          const unsigned x_epoch = (unsigned)(step * NL + l + 1);  // unique per (step, layer): the flags need no reset
+          for (int e = 0; e < x_entries; ++e) {
+            int it, passes;
+            cross_entry(e, it, passes);
             const int b = it / H, h = it - b * H;
-            if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct) * __ldcg(p.rs + MK_R + b);
-            int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
+            float* const xp = p.xp + (size_t)it * (Mp + 4);  // published probabilities of a split item
+            float sum;
+            if (passes & 1) {
+              // ---- K pass: scores of this thread's key pairs, mask, softmax numerators into s_sc
+              if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct) * __ldcg(p.rs + MK_R + b);
+              int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
 #pragma unroll
-            for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
-            cons_sync();
-            float acc[8];
+              for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
+              cons_sync();
+              float acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-            for (int c = 0; c < cross_nkc; ++c) {
-              mk_wait(bar_full + 8 * r.s, r.ph);
-              const uint8_t* buf = ring + (size_t)r.s * MK_STAGE;
-              const int r0 = c * cross_rk, rows = min(cross_rk, 64 - r0);
-              const uint32_t* hrow = reinterpret_cast<const uint32_t*>(buf) + ct;
-              const uint16_t* lrow = reinterpret_cast<const uint16_t*>(buf + (size_t)rows * Mp * 2) + ct;
+              for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+              for (int c = 0; c < cross_nkc; ++c) {
+                mk_wait(bar_full + 8 * r.s, r.ph);
+                const uint8_t* buf = ring + (size_t)r.s * MK_STAGE;
+                const int r0 = c * cross_rk, rows = min(cross_rk, 64 - r0);
+                const uint32_t* hrow = reinterpret_cast<const uint32_t*>(buf) + ct;
+                const uint16_t* lrow = reinterpret_cast<const uint16_t*>(buf + (size_t)rows * Mp * 2) + ct;
 #pragma unroll 2
-              for (int rr = 0; rr < rows; ++rr) {
-                const float qd = s_q[r0 + rr];
-                // pairs >= Mp/2 read past the row (still inside this CTA's shared memory); their sums are never used
+                for (int rr = 0; rr < rows; ++rr) {
+                  const float qd = s_q[r0 + rr];
+                  // pairs >= Mp/2 read past the row (still inside this CTA's shared memory); their sums are never used
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint32_t h2 = hrow[256 * i], l2 = lrow[256 * i];
-                  acc[2 * i] += qd * __uint_as_float(__byte_perm(h2, l2, 0x1046));
-                  acc[2 * i + 1] += qd * __uint_as_float(__byte_perm(h2, l2, 0x3256));
+                  for (int i = 0; i < 4; ++i) {
+                    const uint32_t h2 = hrow[256 * i], l2 = lrow[256 * i];
+                    acc[2 * i] += qd * __uint_as_float(__byte_perm(h2, l2, 0x1046));
+                    acc[2 * i + 1] += qd * __uint_as_float(__byte_perm(h2, l2, 0x3256));
+                  }
+                  hrow += Mp >> 1;
+                  lrow += Mp >> 1;
                 }
-                hrow += Mp >> 1;
-                lrow += Mp >> 1;
+                cons_sync();
+                if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
+                r.adv();
+              }
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
+                const bool ok = m < Mp;
+                acc[i] = ok ? acc[i] + (mk8[i] ? 0.f : -3.4028234663852886e38f) : -INFINITY;
+                mx = fmaxf(mx, acc[i]);
+              }
+              mx = mk_block_reduce(mx, s_b, cw, lane, 1);
+              sum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
+                if (m < Mp) {
+                  const float ev = expf(acc[i] - mx);
+                  s_sc[m] = ev;
+                  if (passes == 1) xp[m] = ev;  // the V pass of this item runs on the next CTA
+                  sum += ev;
+                }
+              }
+              sum = mk_block_reduce(sum, s_b, cw, lane, 0);
+              if (passes == 1) {
+                if (ct == 0) {
+                  xp[Mp] = sum;
+                  __threadfence();  // cumulative: the other threads' stores were ordered before it by the barrier above
+                  atomicExch(p.xflag + it, x_epoch);
+                }
+                continue;
+              }
+            } else {
+              // ---- V pass of an item whose K pass ran on the previous CTA (as ITS first work: long done)
+              if (ct == 0) {
+                unsigned v;
+                const long long t0 = clock64();
+                for (;;) {
+                  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.xflag + it) : "memory");
+                  if (v == x_epoch) break;
+                  if (clock64() - t0 > 4000000000LL) mk_die(5, v, x_epoch);
+                }
               }
               cons_sync();
-              if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
-              r.adv();
+              for (int m = ct; m < Mp; m += 256) s_sc[m] = __ldcg(xp + m);
+              sum = __ldcg(xp + Mp);
+              cons_sync();
             }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
-              const bool ok = m < Mp;
-              acc[i] = ok ? acc[i] + (mk8[i] ? 0.f : -3.4028234663852886e38f) : -INFINITY;
-              mx = fmaxf(mx, acc[i]);
-            }
-            mx = mk_block_reduce(mx, s_b, cw, lane, 1);
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
-              if (m < Mp) {
-                const float e = expf(acc[i] - mx);
-                s_sc[m] = e;
-                sum += e;
-              }
-            }
-            sum = mk_block_reduce(sum, s_b, cw, lane, 0);
+            // ---- V pass
             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int c = 0; c < cross_nvc; ++c) {
               mk_wait(bar_full + 8 * r.s, r.ph);

@@ -947,6 +947,9 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     mp.part_val = part_val; mp.part_idx = part_idx; mp.step_ptr = lanes[0].ctr; mp.mem_mask = mem_mask;
     mp.dec_bias = dec_bias; mp.lut = lut_dec; mp.bar_ctr = mega_bar;
     mp.rs = a.get<float>(3 * 32);
+    mp.xp = a.get<float>((int64_t)B * H * (Mp + 4));
+    mp.xflag = a.get<unsigned>((int64_t)B * H);
+    MG_CHECK_CUDA(cudaMemsetAsync(mp.xflag, 0, sizeof(unsigned) * (size_t)B * H, st));
     mp.dbg_host = pinned_flag + 8;
     for (int i = 8; i < 16; ++i) pinned_flag[i] = 0;
     if (getenv("MG_MEGA_DBG")) mp.dbg = atoi(getenv("MG_MEGA_DBG"));
