@@ -49,7 +49,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   // Persistent: one CTA per SM walks the tile list (tile = blockIdx.x, += gridDim.x).  The shared-memory ring and its
   // barrier phases run on across tiles, and the fp32 accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so the
   // epilogue of tile i (TMEM -> registers -> global) overlaps the MMAs of tile i+1 and the per-tile prologue
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], 128 epilogue threads
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], 256 epilogue threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_empty_bar[i], 256);
     }
     fence_mbar_init();
   }
@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         }
       }
     } else {
-      // ------------------------------------------------------------------ epilogue (warps 2..5)
+      // ------------------------------------------------------------------ epilogue (warps 2..9)
+      // two warps per TMEM lane quadrant, each taking half of the tile's columns: with K = 64 (attention scores)
+      // a tile is one k-block of MMAs and 64 KB of output, and the epilogue's throughput is the kernel's
       const GemmEpilogue& ep = p.ep;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -201,8 +203,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       const int64_t row = (row_ok && ep.row_map) ? ep.row_map[m] : m;
       const int64_t off_b = (int64_t)b1 * ep.bs1 + (int64_t)b2 * ep.bs2;
       const float bias_m = (row_ok && ep.bias && ep.bias_on_rows) ? ep.bias[m] : 0.f;
+      constexpr int CHALF = (BN >= 64) ? BN / 2 : BN;        // columns per warp of a quadrant pair
+      const int c_lo = (BN >= 64) ? ((warp - 2) >> 2) * CHALF : 0;
+      const int c_hi = (BN >= 64 || warp < 6) ? c_lo + CHALF : 0;  // BN = 32: the second warp of a pair has no columns
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores below
@@ -353,7 +358,7 @@ static void launch_bn(cudaStream_t st, const GemmParams& p, dim3 grid) {
     MG_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(p);
+  gemm_tc_kernel<BN><<<grid, 320, Cfg<BN>::SMEM, st>>>(p);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 
