@@ -303,14 +303,18 @@ void launch_relbucket_hv(cudaStream_t st, const double* bbox_ext, int B, int Sp,
 // (UdopStack :1173-1190, RelativePositionBiasAggregated :973-989, UdopAttention :608-613).  The (B,H,S,S)
 // bias tensor of the reference is never materialised: buckets come from `hv` (shared over heads/layers) and
 // an integer LUT over j-i.  One warp per (b,h,i) row; output = split planes for the P*V GEMM.
+#ifndef ENC_SM_THREADS
+#define ENC_SM_THREADS 256
+#define ENC_SM_MINB 2
+#endif
 template <int MAXQ>  // quads (4 consecutive keys) per lane
-__global__ void __launch_bounds__(256) enc_softmax_kernel(const float* __restrict__ scores, const uchar2* __restrict__ hv,
+__global__ void __launch_bounds__(ENC_SM_THREADS, ENC_SM_MINB) enc_softmax_kernel(const float* __restrict__ scores, const uchar2* __restrict__ hv,
                                    const int* __restrict__ mask, const float* __restrict__ tab1d,
                                    const float* __restrict__ tabh, const float* __restrict__ tabv,
                                    const int* __restrict__ lut1d, int lut1d_n, int half_buckets, int nbuckets, int H,
-                                   int Sp, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo) {
+                                   int Sp, bf16* __restrict__ p_hi, bf16* __restrict__ p_lo, int64_t n_rows) {
   extern __shared__ float smf[];
-  // tables transposed to [head][bucket]: a warp works on ONE head, so its lanes index by bucket only and
+  // tables transposed to [head][bucket]: a warp works on ONE head at a time, so its lanes index by bucket only and
   // distinct buckets fall in distinct banks (the [bucket][head] layout of the weights is a 16-way conflict)
   float* t1 = smf;                    // [H*nbuckets]
   float* th = t1 + nbuckets * H;
@@ -324,89 +328,102 @@ __global__ void __launch_bounds__(256) enc_softmax_kernel(const float* __restric
   }
   for (int i = threadIdx.x; i < lut1d_n; i += blockDim.x) l1[i] = lut1d[i];
   __syncthreads();
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b*H + h)*Sp + i
+  // One warp per (image, query row), looping over the heads: the three bucket ids and the mask bit of every key --
+  // the part of the work that does not depend on the head -- are decoded ONCE into a packed word per key and reused
+  // by all H heads (the kernel is instruction-bound: ~40 instructions per score when every head redid the decode).
+  const int64_t rowbi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // b*Sp + i
+  if (rowbi >= n_rows) return;
   const int lane = threadIdx.x & 31;
-  const int i = (int)(row % Sp);
-  const int h = (int)((row / Sp) % H);
-  const int64_t b = row / ((int64_t)Sp * H);
-  const float* t1h = t1 + h * nbuckets;
-  const float* thh = th + h * nbuckets;
-  const float* tvh = tv + h * nbuckets;
-  const float4* sr = reinterpret_cast<const float4*>(scores + row * Sp);
-  const uint2* hvr = reinterpret_cast<const uint2*>(hv + (b * Sp + i) * Sp);   // 4 x uchar2
+  const int i = (int)(rowbi % Sp);
+  const int64_t b = rowbi / Sp;
+  const uint2* hvr = reinterpret_cast<const uint2*>(hv + rowbi * Sp);   // 4 x uchar2
   const int4* mr = reinterpret_cast<const int4*>(mask + b * Sp);
   const int nq = Sp >> 2;  // Sp is a multiple of 8
-  // phase 1: issue every global load of the row before touching the data (memory-level parallelism)
-  float4 v[MAXQ];
-  uint2 hq[MAXQ];
-  int4 mq[MAXQ];
+  uint32_t pk[MAXQ][4];    // bh | bv << 8 | b1 << 16 | visible << 24
 #pragma unroll
   for (int e = 0; e < MAXQ; ++e) {
     const int q = lane + 32 * e;
     if (q < nq) {
-      v[e] = __ldcs(sr + q);   // streamed once
-      hq[e] = __ldg(hvr + q);
-      mq[e] = __ldg(mr + q);
-    }
-  }
-  float mx = -INFINITY;
-#pragma unroll
-  for (int e = 0; e < MAXQ; ++e) {
-    const int q = lane + 32 * e;
-    if (q < nq) {
-      float* vv = reinterpret_cast<float*>(&v[e]);
-      const uint32_t hw[2] = {hq[e].x, hq[e].y};
-      const int mm[4] = {mq[e].x, mq[e].y, mq[e].z, mq[e].w};
+      const uint2 hq = __ldg(hvr + q);
+      const int4 mq = __ldg(mr + q);
+      const uint32_t hw[2] = {hq.x, hq.y};
+      const int mm[4] = {mq.x, mq.y, mq.z, mq.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = q * 4 + k;
-        const uint32_t pr = (hw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-        const int bh = pr & 0xff, bv = pr >> 8;
+        const uint32_t pr = (hw[k >> 1] >> ((k & 1) * 16)) & 0xffffu;  // bh | bv << 8
         int rel = j - i;
         const int o1 = rel > 0 ? half_buckets : 0;
         rel = rel < 0 ? -rel : rel;
         if (rel > lut1d_n - 1) rel = lut1d_n - 1;
-        const int b1 = o1 + l1[rel];
-        float bias = tvh[bv] + (thh[bh] + t1h[b1]);
-        bias = bias + (mm[k] ? 0.f : -3.4028234663852886e38f);
-        vv[k] = vv[k] + bias;
-        mx = fmaxf(mx, vv[k]);
+        pk[e][k] = pr | ((uint32_t)(o1 + l1[rel]) << 16) | (mm[k] ? (1u << 24) : 0u);
       }
     }
   }
-  mx = warp_max(mx);
-  float sum = 0.f;
+  for (int h = 0; h < H; ++h) {
+    const int64_t row = (b * H + h) * Sp + i;
+    const float* t1h = t1 + h * nbuckets;
+    const float* thh = th + h * nbuckets;
+    const float* tvh = tv + h * nbuckets;
+    const float4* sr = reinterpret_cast<const float4*>(scores + row * Sp);
+    // issue every global load of the row before touching the data (memory-level parallelism)
+    float4 v[MAXQ];
 #pragma unroll
-  for (int e = 0; e < MAXQ; ++e) {
-    const int q = lane + 32 * e;
-    if (q < nq) {
-      float* vv = reinterpret_cast<float*>(&v[e]);
+    for (int e = 0; e < MAXQ; ++e) {
+      const int q = lane + 32 * e;
+      if (q < nq) v[e] = __ldcs(sr + q);   // streamed once
+    }
+    float mx = -INFINITY;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        vv[k] = expf(vv[k] - mx);
-        sum += vv[k];
+    for (int e = 0; e < MAXQ; ++e) {
+      const int q = lane + 32 * e;
+      if (q < nq) {
+        float* vv = reinterpret_cast<float*>(&v[e]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t w = pk[e][k];
+          float bias = tvh[(w >> 8) & 0xffu] + (thh[w & 0xffu] + t1h[(w >> 16) & 0xffu]);
+          bias = bias + ((w >> 24) ? 0.f : -3.4028234663852886e38f);
+          vv[k] = vv[k] + bias;
+          mx = fmaxf(mx, vv[k]);
+        }
       }
     }
-  }
-  sum = warp_sum(sum);
-  const float inv_sum = 1.f / sum;
-  uint2* ph = reinterpret_cast<uint2*>(p_hi + row * Sp);
-  uint2* pl = p_lo ? reinterpret_cast<uint2*>(p_lo + row * Sp) : nullptr;
+    mx = warp_max(mx);
+    float sum = 0.f;
 #pragma unroll
-  for (int e = 0; e < MAXQ; ++e) {
-    const int q = lane + 32 * e;
-    if (q < nq) {
-      const float* vv = reinterpret_cast<const float*>(&v[e]);
-      bf16 hh[4], ll[4];
+    for (int e = 0; e < MAXQ; ++e) {
+      const int q = lane + 32 * e;
+      if (q < nq) {
+        float* vv = reinterpret_cast<float*>(&v[e]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) split_bf16(vv[k] * inv_sum, hh[k], ll[k]);
-      uint2 oh, ol;
-      oh.x = (uint32_t)__bfloat16_as_ushort(hh[0]) | ((uint32_t)__bfloat16_as_ushort(hh[1]) << 16);
-      oh.y = (uint32_t)__bfloat16_as_ushort(hh[2]) | ((uint32_t)__bfloat16_as_ushort(hh[3]) << 16);
-      ol.x = (uint32_t)__bfloat16_as_ushort(ll[0]) | ((uint32_t)__bfloat16_as_ushort(ll[1]) << 16);
-      ol.y = (uint32_t)__bfloat16_as_ushort(ll[2]) | ((uint32_t)__bfloat16_as_ushort(ll[3]) << 16);
-      ph[q] = oh;
-      if (pl) pl[q] = ol;
+        for (int k = 0; k < 4; ++k) {
+          vv[k] = expf(vv[k] - mx);
+          sum += vv[k];
+        }
+      }
+    }
+    sum = warp_sum(sum);
+    const float inv_sum = 1.f / sum;
+    uint2* ph = reinterpret_cast<uint2*>(p_hi + row * Sp);
+    uint2* pl = p_lo ? reinterpret_cast<uint2*>(p_lo + row * Sp) : nullptr;
+#pragma unroll
+    for (int e = 0; e < MAXQ; ++e) {
+      const int q = lane + 32 * e;
+      if (q < nq) {
+        const float* vv = reinterpret_cast<const float*>(&v[e]);
+        // fp32 -> bf16 hi + bf16 lo, two elements per conversion (same rounding as split_bf16)
+        const float p0 = vv[0] * inv_sum, p1 = vv[1] * inv_sum, p2 = vv[2] * inv_sum, p3 = vv[3] * inv_sum;
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1), h23 = __floats2bfloat162_rn(p2, p3);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(p0 - f01.x, p1 - f01.y);
+        const __nv_bfloat162 l23 = __floats2bfloat162_rn(p2 - f23.x, p3 - f23.y);
+        uint2 oh, ol;
+        oh.x = *reinterpret_cast<const uint32_t*>(&h01); oh.y = *reinterpret_cast<const uint32_t*>(&h23);
+        ol.x = *reinterpret_cast<const uint32_t*>(&l01); ol.y = *reinterpret_cast<const uint32_t*>(&l23);
+        ph[q] = oh;
+        if (pl) pl[q] = ol;
+      }
     }
   }
 }
@@ -416,20 +433,19 @@ void launch_enc_softmax(cudaStream_t st, const float* scores, const uchar2* hv, 
                         int nbuckets, int B, int H, int Sp, Planes P) {
   MG_REQUIRE(Sp % 8 == 0 && Sp <= 128 * 13, "encoder sequence must be a multiple of 8 and <= 1664");
   MG_REQUIRE(nbuckets <= 256, "too many relative-position buckets");
-  const int64_t rows = (int64_t)B * H * Sp;
-  const int wpb = 8;
-  MG_REQUIRE(rows % wpb == 0, "B*H*Sp must be a multiple of 8");
+  const int64_t rows = (int64_t)B * Sp;  // one warp per (image, query row), all heads
+  const int wpb = ENC_SM_THREADS / 32;
   const size_t smem = (size_t)3 * nbuckets * H * sizeof(float) + (size_t)lut1d_n * sizeof(int);
-  const unsigned grid = (unsigned)(rows / wpb);
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
   if (Sp <= 128 * 5)
     enc_softmax_kernel<5><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
-                                                        half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+                                                        half_buckets, nbuckets, H, Sp, P.hi, P.lo, rows);
   else if (Sp <= 128 * 9)
     enc_softmax_kernel<9><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
-                                                        half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+                                                        half_buckets, nbuckets, H, Sp, P.hi, P.lo, rows);
   else
     enc_softmax_kernel<13><<<grid, wpb * 32, smem, st>>>(scores, hv, mask, tab1d, tabh, tabv, lut1d, lut1d_n,
-                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo);
+                                                         half_buckets, nbuckets, H, Sp, P.hi, P.lo, rows);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 
