@@ -117,6 +117,9 @@ int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kern
  * with CUDA events on the launch stream: total milliseconds, steps executed, and whether the fused persistent
  * decode-step kernel ran (1) or the per-operation kernel chain (0). Host pointers, any may be NULL. */
 int mg_last_decode_loop(mg_model* m, float* loop_ms, int32_t* steps, int32_t* fused);
+/* p50 decode-step latency of the last fused greedy generate: the median, over its 16-step windows, of the mean step
+ * time inside a window (CUDA events between windows on the launch stream); 0 if the kernel chain ran. */
+int mg_last_decode_p50(mg_model* m, float* step_p50_ms);
 
 /* Measurement hook for bench.py: re-launches the decode cross-attention kernel (the dominant, HBM-bound kernel of
  * the path) over the cross-KV buffers of the preceding mg_generate call, every decoder layer in turn (each

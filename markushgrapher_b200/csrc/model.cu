@@ -181,6 +181,8 @@ struct mg_model {
   int last_loop_steps = 0;
   int last_fused = 0;         // 1 if the last greedy generate used the fused persistent decode-step kernel
   cudaEvent_t ev_loop[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_win;  // one event per 16-step window of the fused decode loop (p50 step latency)
+  float last_step_p50_ms = 0.f;
   int64_t last_launches = 0;
   int* pinned_flag = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -218,6 +220,8 @@ struct mg_model {
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     for (auto& e : ev_loop)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : ev_win)
       if (e) cudaEventDestroy(e);
   }
 
@@ -1048,6 +1052,17 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     // two launches per token: nothing to capture, the host simply runs ahead of the GPU
     pinned_flag[0] = pinned_flag[1] = B;
     bool stop = false;
+    size_t n_win = 0;
+    std::vector<int> win_steps;
+    auto mark = [&]() {
+      if (n_win == ev_win.size()) {
+        cudaEvent_t e;
+        MG_CHECK_CUDA(cudaEventCreate(&e));
+        ev_win.push_back(e);
+      }
+      MG_CHECK_CUDA(cudaEventRecord(ev_win[n_win++], st));
+    };
+    mark();
     try {
     while (done_steps < total_steps && !stop) {
       const int n = std::min(16, total_steps - done_steps);
@@ -1055,11 +1070,24 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
         one_step(lanes[0]);
         if (dist) exchange(done_steps + i + 1);
       }
+      mark();
+      win_steps.push_back(n);
       done_steps += n;
       MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));  // poll the "all finished" counter one window late
       if (pinned_flag[0] == 0) stop = true;
       MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? gctr + 3 : lanes[0].ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
       MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
+    }
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));
+    {  // median over the windows of the mean step latency inside a window
+      std::vector<float> per;
+      for (size_t w = 0; w + 1 < n_win; ++w) {
+        float ms = 0.f;
+        MG_CHECK_CUDA(cudaEventElapsedTime(&ms, ev_win[w], ev_win[w + 1]));
+        per.push_back(ms / (float)win_steps[w]);
+      }
+      std::sort(per.begin(), per.end());
+      last_step_p50_ms = per.empty() ? 0.f : per[per.size() / 2];
     }
     } catch (const Error& e) {
       if (pinned_flag[8] != 0)  // the fused kernel's watchdog fired: say where
@@ -1508,6 +1536,13 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
     *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->cur_M * d * (m->prof_kv24 ? 3 : 4) + (int64_t)m->cur_M * 4 +
                                       (int64_t)d * 4 + (int64_t)d * (m->split2 ? 4 : 2));
   if (n_launches) *n_launches = reps * NL;
+  MG_API_END
+}
+
+int mg_last_decode_p50(mg_model* m, float* step_p50_ms) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (step_p50_ms) *step_p50_ms = m->last_step_p50_ms;
   MG_API_END
 }
 

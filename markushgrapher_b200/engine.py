@@ -96,6 +96,7 @@ class MGEngine:
                                        [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3)
         L.mg_last_stats.argtypes = [ctypes.c_void_p] * 4
         L.mg_last_decode_loop.argtypes = [ctypes.c_void_p] * 4
+        L.mg_last_decode_p50.argtypes = [ctypes.c_void_p] * 2
         L.mg_destroy.argtypes = [ctypes.c_void_p]
         L.mg_destroy.restype = None
         self.n_patches = (cfg.image_size // cfg.patch_size) ** 2
@@ -237,7 +238,9 @@ class MGEngine:
         ms, n, f = ctypes.c_float(0), ctypes.c_int32(0), ctypes.c_int32(0)
         _lib.check(_lib.lib().mg_last_decode_loop(self._h, ctypes.addressof(ms), ctypes.addressof(n),
                                                   ctypes.addressof(f)), "mg_last_decode_loop")
-        return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value)}
+        p50 = ctypes.c_float(0)
+        _lib.check(_lib.lib().mg_last_decode_p50(self._h, ctypes.addressof(p50)), "mg_last_decode_p50")
+        return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value), "step_p50_ms": p50.value}
 
     def last_stats(self):
         e, d, k = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int64(0)
