@@ -127,7 +127,14 @@ struct RingPos {
   }
 };
 
-__device__ __forceinline__ int mega_lin_of_phase(int ph) { return ph == 0 ? 0 : (ph < 4 ? ph - 1 : ph - 2); }  // 0,2,3,5,6,7 -> 0..5
+// Phases of a decoder layer: 0 qkv (+ the x part of the cross query), 1 self-attention, 2 o (+ the ctx part of the
+// cross query), 3 cross-attention, 4 co, 5 wi, 6 wo.  The cross query q = Wcq' (x + Wo ctx), Wcq' = Wcq diag(ln2), is
+// linear in its two inputs, so it is accumulated as Wcq' x (extra rows of phase 0, same activation tile as q/k/v) plus
+// (Wcq' Wo) ctx (extra rows of phase 2, same activation tile as o; the 1024^2 product is precomputed at finalize):
+// the separate "cq" phase of the kernel chain -- a whole latency-bound linear and its grid barrier -- is gone.
+constexpr int MK_NPH = 7;
+constexpr int MK_PH_SELF = 1, MK_PH_CROSS = 3;
+__device__ __forceinline__ int mega_lin_of_phase(int ph) { return ph == 0 ? 0 : (ph == 2 ? 1 : ph - 2); }  // 0,2,4,5,6 -> 0..4
 __device__ __forceinline__ int items_of_cta(int total, int g, int G) { return g < total ? (total - g + G - 1) / G : 0; }
 // k-blocks of work item `it` of a linear
 __device__ __forceinline__ int lin_item_kbs(const MegaLin& W, int it, int& tile, int& kb0) {
@@ -256,9 +263,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
       for (int l = 0; l <= NL; ++l) {
         const MegaLayer& L = s_layers[min(l, NL - 1)];
-        const int nph = l < NL ? 8 : 1;
+        const int nph = l < NL ? MK_NPH : 1;
         for (int ph = 0; ph < nph; ++ph) {
-          const bool attn = l < NL && (ph == 1 || ph == 4);
+          const bool attn = l < NL && (ph == MK_PH_SELF || ph == MK_PH_CROSS);
           int n_items, div = 1, units = 1, upi = 1;  // item -> (major = it / div, minor = it % div)
           const uint8_t* base0;
           const uint8_t* base1 = nullptr;
@@ -268,13 +275,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           if (attn) {
             if (p.gate) {
               // prefetch gate: this phase's K/V stream starts when the CTA's consumers have entered the phase
-              const int want = l * 8 + ph;
+              const int want = l * MK_NPH + ph;
               const long long t0 = clock64();
               while (*s_phase < want)
                 if (clock64() - t0 > 4000000000LL) mk_die(2, want, *s_phase);
             }
             n_items = n_attn;
-            if (ph == 1) {
+            if (ph == MK_PH_SELF) {
               base0 = reinterpret_cast<const uint8_t*>(L.skb); sa0 = (size_t)Tb * 8192; tot0 = (uint32_t)self_nblk * 8192u;
               chunk0 = MK_SELF_KB * 8192;
               base1 = reinterpret_cast<const uint8_t*>(L.svb); sa1 = (size_t)p.Tp * 256; tot1 = (uint32_t)step * 256u;
@@ -295,8 +302,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // items are issued in bundles: the self-attention phase processes MK_SELF_NG items concurrently, so their
           // chunks are interleaved (chunk c of every item of the bundle, then chunk c+1, ...); elsewhere bundle = 1
           const int stride = attn ? Ga : G;
-          const int bundle = (attn && ph == 1) ? MK_SELF_NG : 1;
-          const bool is_cross = attn && ph == 4;
+          const int bundle = (attn && ph == MK_PH_SELF) ? MK_SELF_NG : 1;
+          const bool is_cross = attn && ph == MK_PH_CROSS;
           for (int e = 0, it0 = attn ? attn_first : g; is_cross ? e < x_entries : it0 < n_items; ++e, it0 += stride * bundle) {
             int passes = 3;
             if (is_cross) cross_entry(e, it0, passes);
@@ -357,14 +364,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
 #endif
       for (int l = 0; l <= NL; ++l) {
         const MegaLayer& L = s_layers[min(l, NL - 1)];
-        const int nph = l < NL ? 8 : 1;
+        const int nph = l < NL ? MK_NPH : 1;
         for (int ph = 0; ph < nph; ++ph) {
-          if (l < NL && ph == 1) { r.adv_n(my_attn * (self_nkc + self_nvc)); continue; }
-          if (l < NL && ph == 4) { r.adv_n((x_whole + x_lone_k) * cross_nkc + (x_whole + x_lone_v) * cross_nvc); continue; }
+          if (l < NL && ph == MK_PH_SELF) { r.adv_n(my_attn * (self_nkc + self_nvc)); continue; }
+          if (l < NL && ph == MK_PH_CROSS) { r.adv_n((x_whole + x_lone_k) * cross_nkc + (x_whole + x_lone_v) * cross_nvc); continue; }
           const MegaLin& W = l < NL ? L.lin[mega_lin_of_phase(ph)] : p.lm_head;
           const int items = W.tiles * W.ksplit;
 #ifdef MK_FINE
-          unsigned long long* fm = (p.prof && mma_phase >= 6 && mma_phase < 12) ? p.prof + ((size_t)g * 512 + 400 + (mma_phase - 6) * 4) * 2 : nullptr;
+          unsigned long long* fm = (p.prof && mma_phase >= 5 && mma_phase < 10) ? p.prof + ((size_t)g * 512 + 400 + (mma_phase - 5) * 4) * 2 : nullptr;
           ++mma_phase;
 #endif
           for (int it = g; it < items; it += G) {
@@ -423,9 +430,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
 
     for (int l = 0; l <= NL; ++l) {
       const MegaLayer& L = s_layers[min(l, NL - 1)];
-      const int nph = l < NL ? 8 : 1;
+      const int nph = l < NL ? MK_NPH : 1;
       for (int ph = 0; ph < nph; ++ph) {
-        if (l < NL && ph == 1) {
+        if (l < NL && ph == MK_PH_SELF) {
           // ---------------------------------------------------------------------------------- self-attention
           // fused KV-cache append + single-query attention with the T5 unidirectional bucket bias (no 1/sqrt(d)).
           // K cache [b][h][key/32][64 d][32 keys] (contiguous per (image, head), conflict-free thread = key),
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             }
             r.adv_n(nch * ng);
           }
-        } else if (l < NL && ph == 4) {
+        } else if (l < NL && ph == MK_PH_CROSS) {
           // ---------------------------------------------------------------------------------- cross-attention
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
           // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = pair of adjacent keys.
@@ -590,7 +597,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             float sum;
             if (passes & 1) {
               // ---- K pass: scores of this thread's key pairs, mask, softmax numerators into s_sc
-              if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct) * __ldcg(p.rs + MK_R + b);
+              // q is the UNSCALED cross query (accumulated by phases 0 and 2); its RMSNorm row scale
+              // rsqrt(mean(x[b]^2) + eps) -- x is complete only since the barrier before this phase -- multiplies the
+              // scores after the K stream: each thread fetches 4 of the D <= 1024 residual values now, the block
+              // reduces them once the K pass is over, so the loads' latency hides under the stream.
+              if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct);
+              float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (4 * ct < D) xr = ldcg4(p.x + (int64_t)b * D + 4 * ct);
               int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
 #pragma unroll
               for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
@@ -621,12 +634,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                 if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
                 r.adv();
               }
+              const float rsb = rsqrtf(mk_block_reduce((xr.x * xr.x + xr.y * xr.y) + (xr.z * xr.z + xr.w * xr.w), s_b, cw, lane, 0) / (float)D + p.eps);
               float mx = -INFINITY;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
                 const bool ok = m < Mp;
-                acc[i] = ok ? acc[i] + (mk8[i] ? 0.f : -3.4028234663852886e38f) : -INFINITY;
+                acc[i] = ok ? acc[i] * rsb + (mk8[i] ? 0.f : -3.4028234663852886e38f) : -INFINITY;
                 mx = fmaxf(mx, acc[i]);
               }
               mx = mk_block_reduce(mx, s_b, cw, lane, 1);
@@ -701,34 +715,36 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // ---------------------------------------------------------------------------------- linear
           // out[b][n] (+)= sum_k pro(x)[b][k] * W[n][k];  pro: 0 none, 1 RMSNorm weight (x*lnw staged; the row scale
           // rs[b] = rsqrt(mean(x^2)+eps) is NOT applied here: it is computed off the critical path by one warp per
-          // image, published through p.rs, and applied by the consumer of this phase's output -- q/k/v and the
-          // cross query when they are loaded, the FF hidden activations as relu(rs*h) = rs*relu(h)), 2 ReLU * rs.
+          // image, published through p.rs, and applied by the consumer of this phase's output -- q/k/v when they are
+          // loaded, the FF hidden activations as relu(rs*h) = rs*relu(h); the cross query's row scale is computed by
+          // the cross-attention phase itself, under its K stream), 2 ReLU * rs.
           // LM head only: rs * d_model^-0.5 applied in the epilogue (the logits are the final output).
           // (input, prologue, output, which buffer this phase zeroes for a later one):
-          int pro = 1, ldx = D, ld_out = D, rs_slot = -1;
+          int pro = 1, ldx = D, ld_out = D, ld_out2 = D, rs_slot = -1;
           const float* x = p.x;
           float* out = p.x;
+          float* out2 = p.q;  // rows >= W.n_split of a two-output linear (phases 0 and 2) go to the cross query
           const float* lnw = nullptr;
           float* zero_ptr = nullptr;
           int64_t zero_n = 0;
           const bool store = l == NL;
           if (store) {  // LM head: final RMSNorm * d_model^-0.5 fused, direct store + per-tile argmax
             lnw = p.final_ln; out = p.logits; ld_out = p.ld_logits;
-          } else if (ph == 0) {  // x -> qkv (RMSNorm ln1); zero: FF hidden buffer
-            lnw = L.ln[0]; out = p.qkv; ld_out = 3 * D; zero_ptr = p.hbuf; zero_n = (int64_t)B * p.DFF; rs_slot = 0;
-          } else if (ph == 2 || ph == 5) {  // ctx -> x (+=): attention output projections
+          } else if (ph == 0) {  // raw x -> qkv | q (ln1 / ln2 are folded into the weight rows); zero: FF hidden buffer
+            pro = 0; out = p.qkv; ld_out = 3 * D; zero_ptr = p.hbuf; zero_n = (int64_t)B * p.DFF; rs_slot = 0;
+          } else if (ph == 2) {  // self-attention ctx -> x (+=) | q (+=); zero: qkv (consumed by phase 1)
+            pro = 0; x = p.ctx; zero_ptr = p.qkv; zero_n = (int64_t)B * 3 * D;
+          } else if (ph == 4) {  // cross-attention ctx -> x (+=)
             pro = 0; x = p.ctx;
-          } else if (ph == 3) {  // x -> q (RMSNorm ln2); zero: qkv
-            lnw = L.ln[1]; out = p.q; zero_ptr = p.qkv; zero_n = (int64_t)B * 3 * D; rs_slot = 1;
-          } else if (ph == 6) {  // x -> hidden (RMSNorm ln3); zero: q
+          } else if (ph == 5) {  // x -> hidden (RMSNorm ln3); zero: q (consumed by phase 3)
             lnw = L.ln[2]; out = p.hbuf; ld_out = p.DFF; zero_ptr = p.q; zero_n = (int64_t)B * D; rs_slot = 2;
-          } else {  // ph == 7: rs * relu(hidden) -> x (+=)
+          } else {  // ph == 6: rs * relu(hidden) -> x (+=)
             pro = 2; x = p.hbuf; ldx = p.DFF;
           }
           const MegaLin& W = l < NL ? L.lin[mega_lin_of_phase(ph)] : p.lm_head;
           const int items = W.tiles * W.ksplit;
 #ifdef MK_FINE
-          unsigned long long* fine = (p.prof && ct == 0 && phase_i >= 8 && phase_i < 16) ? p.prof + ((size_t)g * 512 + 256 + (phase_i - 8) * 16) * 2 : nullptr;
+          unsigned long long* fine = (p.prof && ct == 0 && phase_i >= MK_NPH && phase_i < 2 * MK_NPH) ? p.prof + ((size_t)g * 512 + 256 + (phase_i - MK_NPH) * 16) * 2 : nullptr;
 #endif
           MK_STAMP(fine, 0);
           if (!is_worker) {
@@ -848,15 +864,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             MK_STAMP(fine, 4);
             tc_fence_after();
             const int q = warp & 3;
-            const int n = tile * 128 + q * 32 + lane;
-            const bool n_ok = n < W.N;
+            int n = tile * 128 + q * 32 + lane, n_lim = W.N, ldo = ld_out;
+            float* o_base = out;
+            if (W.n_split) {  // two-output linear, CTA-uniform branch (n_split is a multiple of the tile height)
+              if (tile * 128 >= W.n_split) { n -= W.n_split; n_lim = W.N - W.n_split; o_base = out2; ldo = ld_out2; }
+              else n_lim = W.n_split;
+            }
+            const bool n_ok = n < n_lim;
             if (!store) {
               // split-K partial sums: red.global.add into the next buffer / the residual stream.  All 8 consumer
               // warps take part: two warps per TMEM lane quadrant, 16 of the 32 image columns each (this loop runs
               // with one warp per scheduler, so its length in instructions is what the phase waits for).
               const int c_lo = (cw >> 2) * 16;
               const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c_lo;
-              float* op = out + (int64_t)c_lo * ld_out + n;
+              float* op = o_base + (int64_t)c_lo * ldo + n;
 #pragma unroll 1
               for (int c = 0; c < 2; ++c) {
                 uint32_t rr[8];
@@ -869,15 +890,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                       atomicAdd(pj, __uint_as_float(rr[j]));
-                      pj += ld_out;
+                      pj += ldo;
                     }
                   } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                      if (j < nv) atomicAdd(op + (int64_t)j * ld_out, __uint_as_float(rr[j]));
+                      if (j < nv) atomicAdd(op + (int64_t)j * ldo, __uint_as_float(rr[j]));
                   }
                 }
-                op += (int64_t)8 * ld_out;
+                op += (int64_t)8 * ldo;
               }
               tc_fence_before();
               mk_arrive(bar_tempty);
@@ -989,9 +1010,11 @@ __global__ void tile_weights_kernel(const bf16* __restrict__ hi, const bf16* __r
   }
 }
 
-MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst) {
+MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst, int n_split) {
+  MG_REQUIRE(n_split % 128 == 0 && n_split < N, "fused decode step: output split must be a multiple of the 128-row tile");
   MegaLin L;
   L.N = N;
+  L.n_split = n_split;
   L.K = K;
   L.tiles = (N + 127) / 128;
   L.num_kb = K / 64;
@@ -1005,6 +1028,40 @@ MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool
   tile_weights_kernel<<<blocks, 256, 0, st>>>(w.hi, w.lo, N, K, ldk, L.tiles, L.num_kb, dst);
   MG_CHECK_CUDA(cudaGetLastError());
   return L;
+}
+
+// ------------------------------------------------------------------------------------------------ folded cross query
+// finalize-time, once per layer: gain folding and the Wcq' Wo product of the two-output linears (phases 0 and 2)
+__global__ void scale_cols_kernel(const float* __restrict__ src, const float* __restrict__ gain, int64_t total, int K,
+                                  float* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * gain[i % K];
+}
+void launch_scale_cols(cudaStream_t st, const float* src, const float* gain, int rows, int K, float* dst) {
+  const int64_t total = (int64_t)rows * K;
+  scale_cols_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(src, gain, total, K, dst);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+// P[n][j] = sum_k A[n][k] * Bm[k][j], row-major, fp64 accumulation (the result is rounded to fp32 once); 32x32 tiles
+__global__ void fold_product_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int N, int K, int J,
+                                    float* __restrict__ P) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int n = blockIdx.y * 32 + ty, j = blockIdx.x * 32 + tx;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    sa[ty][tx] = (n < N && k0 + tx < K) ? A[(int64_t)n * K + k0 + tx] : 0.f;
+    sb[ty][tx] = (k0 + ty < K && j < J) ? Bm[(int64_t)(k0 + ty) * J + j] : 0.f;
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) acc += (double)sa[ty][k] * (double)sb[k][tx];
+    __syncthreads();
+  }
+  if (n < N && j < J) P[(int64_t)n * J + j] = (float)acc;
+}
+void launch_fold_product(cudaStream_t st, const float* A, const float* Bm, int N, int K, int J, float* P) {
+  fold_product_kernel<<<dim3((J + 31) / 32, (N + 31) / 32), dim3(32, 32), 0, st>>>(A, Bm, N, K, J, P);
+  MG_CHECK_CUDA(cudaGetLastError());
 }
 
 size_t mega_lin_bytes(int N, int K) { return (size_t)((N + 127) / 128) * (K / 64) * MK_WTILE; }
@@ -1026,7 +1083,7 @@ int mega_max_ctas() {
 void launch_decode_step(cudaStream_t st, const MegaParams& p, int n_ctas) {
   MG_REQUIRE(p.B >= 1 && p.B <= MK_R, "fused decode step: 1 <= B <= 32");
   MG_REQUIRE(p.Mp % 8 == 0 && p.Mp <= MK_MAXSC && p.Tp % 32 == 0 && p.Tp <= 512, "fused decode step: Mp / max_length out of range");
-  MG_REQUIRE(p.D == p.H * 64 && p.D <= 1024 && p.D % 64 == 0 && p.DFF % 64 == 0, "fused decode step: unsupported dims");
+  MG_REQUIRE(p.D == p.H * 64 && p.D <= 1024 && p.D % 128 == 0 && p.DFF % 64 == 0, "fused decode step: unsupported dims");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_ctas);
   cfg.blockDim = dim3(MK_THREADS);

@@ -110,10 +110,12 @@ struct MegaLin {           // a linear layer as a stream of pre-swizzled 32 KB (
   int N = 0, K = 0;
   int tiles = 0, num_kb = 0;
   int kb_per_item = 0, ksplit = 0;  // work items = tiles * ksplit, item -> (tile = it / ksplit, k-slice = it % ksplit)
+  int n_split = 0;  // two-output linears: rows [0, n_split) go to the first output, [n_split, N) to the second (0 = one output)
+  int pad_ = 0;
 };
 struct MegaLayer {
-  MegaLin lin[6];      // qkv, o, cq, co, wi, wo
-  const float* ln[3];  // RMSNorm weights before qkv / cq / wi
+  MegaLin lin[5];      // qkv|cq_x (ln1 / ln2 folded into the rows), o|cq_ctx, co, wi, wo -- decode_mega.cu phase table
+  const float* ln[3];  // RMSNorm weights before qkv / cq / wi (the kernel reads only ln[2]; the others are folded)
   float* skb;        // self K cache [B][H][Tp/32][64][32]
   float* svb;        // self V cache [B][H][Tp][64]
   const uint8_t* ckv;  // cross K/V, kv24 blocks [B][H][384 * Mp] (decode.cu)
@@ -146,7 +148,10 @@ struct MegaParams {
 };
 size_t mega_lin_bytes(int N, int K);
 // tiles the planes of one linear into dst (mega_lin_bytes(N, K) bytes) and fills the work split for n_ctas CTAs
-MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst);
+MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst, int n_split = 0);
+// finalize-time helpers of the folded cross query: dst[r][k] = src[r][k] * gain[k];  P[n][j] = sum_k A[n][k] * Bm[k][j] (fp64 accumulation)
+void launch_scale_cols(cudaStream_t st, const float* src, const float* gain, int rows, int K, float* dst);
+void launch_fold_product(cudaStream_t st, const float* A, const float* Bm, int N, int K, int J, float* P);
 int mega_max_ctas();  // CTAs of the cooperative launch (= SM count), 0 if the device cannot run it
 void launch_decode_step(cudaStream_t st, const MegaParams& p, int n_ctas);
 

@@ -465,10 +465,12 @@ void mg_model::finalize(cudaStream_t st) {
   {
     const char* mode = getenv("MG_DECODE");
     const bool want = !(mode && std::string(mode) == "chain");
-    mega_ctas = (want && split2) ? mega_max_ctas() : 0;
+    mega_ctas = (want && split2 && d % 128 == 0) ? mega_max_ctas() : 0;  // two-output linears split on 128-row tiles
     if (mega_ctas > 0) {
       const int NL = c.num_decoder_layers, dff = c.d_ff;
-      size_t per_layer = mega_lin_bytes(3 * d, d) + 3 * mega_lin_bytes(d, d) + mega_lin_bytes(dff, d) + mega_lin_bytes(d, dff);
+      // phases 0 and 2 are two-output linears: [Wqkv diag(ln1); Wcq diag(ln2)] on x and [Wo; (Wcq diag(ln2)) Wo] on the
+      // self-attention context together give the cross query (decode_mega.cu); built here from the fp32 weights
+      size_t per_layer = mega_lin_bytes(4 * d, d) + mega_lin_bytes(2 * d, d) + mega_lin_bytes(d, d) + mega_lin_bytes(dff, d) + mega_lin_bytes(d, dff);
       uint8_t* buf = own<uint8_t>((int64_t)(per_layer * NL + mega_lin_bytes(V, d)));
       mega_layers.resize(NL);
       auto tile = [&](const LinearW& W, bool store) {
@@ -476,14 +478,41 @@ void mg_model::finalize(cudaStream_t st) {
         buf += mega_lin_bytes(W.N, W.K);
         return L;
       };
+      float* fold = nullptr;  // [4d][d] fp32 scratch + planes of the same shape, freed below
+      bf16* fold_pl = nullptr;
+      const int64_t ldk = rup(d, 8);
+      MG_CHECK_CUDA(cudaMalloc((void**)&fold, sizeof(float) * (size_t)4 * d * d));
+      MG_CHECK_CUDA(cudaMalloc((void**)&fold_pl, sizeof(bf16) * (size_t)2 * 4 * d * ldk));
+      const Planes fp{fold_pl, fold_pl + (int64_t)4 * d * ldk};
+      auto tile_fold = [&](int N, int n_split) {
+        launch_split(st, fold, N, d, d, fp, ldk);
+        MegaLin L = make_mega_lin(st, fp, N, d, ldk, false, mega_ctas, buf, n_split);
+        buf += mega_lin_bytes(N, d);
+        return L;
+      };
       for (int i = 0; i < NL; ++i) {
         MegaLayer& M = mega_layers[i];
         const DecLayer& L = dec[i];
-        M.lin[0] = tile(L.qkv, false); M.lin[1] = tile(L.o, false); M.lin[2] = tile(L.cq, false);
-        M.lin[3] = tile(L.co, false); M.lin[4] = tile(L.wi, false); M.lin[5] = tile(L.wo, false);
+        const std::string p = "decoder.block." + std::to_string(i) + ".layer.";
+        const char* qkv_names[3] = {"0.SelfAttention.q.weight", "0.SelfAttention.k.weight", "0.SelfAttention.v.weight"};
+        for (int j = 0; j < 3; ++j) {
+          const RawWeight& w = need(p + qkv_names[j]);
+          MG_REQUIRE(w.numel() == (int64_t)d * d, "decoder self-attention weight is not [d_model, d_model]");
+          launch_scale_cols(st, w.ptr, L.ln1, d, d, fold + (int64_t)j * d * d);
+        }
+        launch_scale_cols(st, need(p + "1.EncDecAttention.q.weight").ptr, L.ln2, d, d, fold + (int64_t)3 * d * d);
+        M.lin[0] = tile_fold(4 * d, 3 * d);
+        // rows [d, 2d) = (Wcq diag(ln2)) Wo, from the scaled copy still in fold rows [3d, 4d)
+        launch_fold_product(st, fold + (int64_t)3 * d * d, need(p + "0.SelfAttention.o.weight").ptr, d, d, d, fold + (int64_t)d * d);
+        MG_CHECK_CUDA(cudaMemcpyAsync(fold, need(p + "0.SelfAttention.o.weight").ptr, sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToDevice, st));
+        M.lin[1] = tile_fold(2 * d, d);
+        M.lin[2] = tile(L.co, false); M.lin[3] = tile(L.wi, false); M.lin[4] = tile(L.wo, false);
         M.ln[0] = L.ln1; M.ln[1] = L.ln2; M.ln[2] = L.ln3;
         M.skb = M.svb = nullptr; M.ckv = nullptr; M.pad_ = nullptr;
       }
+      MG_CHECK_CUDA(cudaStreamSynchronize(st));
+      MG_CHECK_CUDA(cudaFree(fold));
+      MG_CHECK_CUDA(cudaFree(fold_pl));
       mega_lm = tile(lm_head, true);
       mega_layers_dev = own<MegaLayer>(NL);
       mega_bar = own<unsigned>(4);
