@@ -387,8 +387,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               mk_wait(bar_xrdy + 8 * r.s, (r.xmask >> r.s) & 1u);
               r.xmask ^= 1u << r.s;
               if (kb == 0) MK_STAMP(fm, 1);
+              if (kb == nkb - 1) MK_STAMP(fm, 4);
               mk_wait(bar_full + 8 * r.s, r.ph);
               if (kb == 0) MK_STAMP(fm, 2);
+              if (kb == nkb - 1) MK_STAMP(fm, 5);
               tc_fence_after();
               const uint32_t sa = ring_a + (uint32_t)r.s * MK_STAGE;
               const uint64_t da_hi = make_sw128_kmajor_desc(sa), da_lo = make_sw128_kmajor_desc(sa + 16384);
@@ -589,6 +591,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
           // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = pair of adjacent keys.
           const unsigned x_epoch = (unsigned)(step * NL + l + 1);  // unique per (step, layer): the flags need no reset
+          int rs_b = -1;    // image whose row scale rsb holds: consecutive entries are mostly heads of one image
+          float rsb = 0.f;
           for (int e = 0; e < x_entries; ++e) {
             int it, passes;
             cross_entry(e, it, passes);
@@ -603,7 +607,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               // reduces them once the K pass is over, so the loads' latency hides under the stream.
               if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct);
               float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (4 * ct < D) xr = ldcg4(p.x + (int64_t)b * D + 4 * ct);
+              const bool new_b = b != rs_b;  // CTA-uniform
+              if (new_b && 4 * ct < D) xr = ldcg4(p.x + (int64_t)b * D + 4 * ct);
               int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
 #pragma unroll
               for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
@@ -634,7 +639,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                 if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
                 r.adv();
               }
-              const float rsb = rsqrtf(mk_block_reduce((xr.x * xr.x + xr.y * xr.y) + (xr.z * xr.z + xr.w * xr.w), s_b, cw, lane, 0) / (float)D + p.eps);
+              if (new_b) {
+                rsb = rsqrtf(mk_block_reduce((xr.x * xr.x + xr.y * xr.y) + (xr.z * xr.z + xr.w * xr.w), s_b, cw, lane, 0) / (float)D + p.eps);
+                rs_b = b;
+              }
               float mx = -INFINITY;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {

@@ -36,12 +36,12 @@ raw = a
 lin = [(0, "qkv|cq"), (2, "o|cq"), (4, "co"), (5, "wi"), (6, "wo")]
 if raw[:, 256:384].any():
     print("\nlinear phases of layer 1 (us since the worker's phase start; mean over CTAs with work)")
-    print(f"{'phase':6s} {'x loaded':>9s} {'staged':>9s} {'rs sync':>9s} {'tmem full':>9s} {'epi done':>9s} {'stat done':>9s} | {'mma:xrdy':>9s} {'W full':>9s} {'commit':>9s} | start-exit")
+    print(f"{'phase':6s} {'x loaded':>9s} {'staged':>9s} {'rs sync':>9s} {'tmem full':>9s} {'epi done':>9s} {'stat done':>9s} | {'mma:xrdy':>9s} {'W full':>9s} {'commit':>9s} {'xrdy last':>9s} {'W last':>9s} | start-exit")
     for j, (k, nm) in enumerate(lin):
         f = raw[:, 256 + k * 16:256 + k * 16 + 16, :].reshape(G, 32)
         fm = raw[:, 400 + j * 4:400 + j * 4 + 4, :].reshape(G, 8)
         ok = (f[:, 5] > 0) & (fm[:, 3] > 0)
         base = f[ok, 0]
         ex = raw[ok, NPH + k - 1, 1]
-        cols = [(f[ok, i] - base).mean() / 1e3 for i in (1, 2, 3, 4, 5, 10)] + [(fm[ok, i] - base).mean() / 1e3 for i in (1, 2, 3)]
+        cols = [(f[ok, i] - base).mean() / 1e3 for i in (1, 2, 3, 4, 5, 10)] + [(fm[ok, i] - base).mean() / 1e3 for i in (1, 2, 3, 4, 5)]
         print(f"{nm:6s} " + " ".join(f"{c:9.2f}" for c in cols[:6]) + " | " + " ".join(f"{c:9.2f}" for c in cols[6:]) + f" | {(base - ex).mean() / 1e3:6.2f}")
