@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/dist_check.py : every rank decodes its shard, the per-step NCCL all-gather
+"""torchrun --nproc-per-node N tests/dist_check.py : every rank decodes its shard, the per-step NCCL all-gather
 must give every rank the ids of the whole batch == the oracle's ids for the whole batch."""
 import os
 import sys
