@@ -108,7 +108,9 @@ int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* i
 /* Decode-path switches (environment, read when the model is finalised / at every generate call):
  *   MG_DECODE=chain  use the per-operation kernel chain (CUDA-graph replayed) instead of the fused persistent
  *                    decode-step kernel, which is the default whenever B <= 32 and max_length <= 512;
- *   MG_KV24=0        keep the cross K/V in fp32 (kernel chain only). */
+ *   MG_KV24=0        keep the cross K/V in fp32 (kernel chain only);
+ *   MG_MEGA_L2PF=<KB> bytes of the coming cross-attention phase each CTA of the fused kernel prefetches into L2
+ *                    (default 384, 0 = off; timing only, results identical). */
 
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);

@@ -144,6 +144,11 @@ struct MegaParams {
   int* dbg_host = nullptr;  // host-mapped pinned words for the watchdog's diagnostics (may be null)
   int dbg = 0;           // profiling builds (-DMK_FINE) only: 1 = skip the reductions, 2 = skip the TMEM loads
   int max_inflight = 5;  // bulk loads one SM keeps in flight (<= ring stages)
+  // decode_mega.cu, producer: paced L2 prefetch of the first bytes of the coming cross-attention phase (0 = off)
+  int l2pf = 384 * 1024;   // bytes per CTA and layer
+  int l2pf_piece = 4096;   // bytes per prefetch instruction (multiple of 16)
+  int l2pf_gap = 500;      // minimum cycles between two prefetch instructions of a CTA
+  int l2pf_mask = 0x07;    // phases (bit = phase index) during whose loads the producer may prefetch
   unsigned long long* prof = nullptr;  // debug: [CTAs][256][2] globaltimer at (work done, barrier passed) per phase
 };
 size_t mega_lin_bytes(int N, int K);
