@@ -269,23 +269,26 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
       // the prefetch never forms a burst in front of the latency-critical activation loads of the linears (an
       // un-paced version issued on phase entry cost exactly the HBM time of the prefetched bytes).
       // The K/V blocks of consecutive items are contiguous in memory, so the CTA's half-works are plain byte ranges;
-      // the cursor follows the order the CTA consumes them.  Measured: -1.0 % step time, -1.6 % p50.
+      // the cursor follows the order the CTA consumes them.  Measured (DESIGN.md decision 9): -0.75 % step time from
+      // spinning on test_wait instead of the suspending try_wait in these phases (the self-attention phase's small
+      // dependent chunks get their slots re-issued sooner), another -0.3 % from the prefetch; -1.6 % p50.
       const uint32_t pf_hw = (uint32_t)Mp * 192u;  // bytes of one half-work (K or V block of one item)
       const uint32_t pf_total = min((uint32_t)p.l2pf, (uint32_t)(xh_hi - xh_lo) * pf_hw);
       uint32_t pf_cur = 0;
       long long pf_last = 0;
       const uint8_t* pf_ckv = nullptr;
       bool pf_on = false;
+      const bool poll_all = (p.l2pf_mask & 0x100) != 0;  // busy-poll (test_wait) for a free slot in every phase
       auto wait_slot = [&](uint32_t bar, uint32_t parity) {
-        if (!(pf_on && pf_cur < pf_total)) { mk_wait(bar, parity); return; }
+        if (!(poll_all || (pf_on && pf_cur < pf_total))) { mk_wait(bar, parity); return; }
         uint32_t done, spins = 0;
         for (;;) {
           asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
           if (done) break;
-          if (pf_cur < pf_total) {
+          if (pf_on && pf_cur < pf_total) {
             const long long now = clock64();
-            if (now - pf_last >= (long long)p.l2pf_gap) {
+            if (p.l2pf_piece > 0 && now - pf_last >= (long long)p.l2pf_gap) {  // piece 0: poll only (A/B of the wait style)
               pf_last = now;
               const uint32_t j = pf_cur / pf_hw, off = pf_cur - j * pf_hw;
               int hw;  // j-th half-work in consumption order -> index in memory order

@@ -148,7 +148,7 @@ struct MegaParams {
   int l2pf = 384 * 1024;   // bytes per CTA and layer
   int l2pf_piece = 4096;   // bytes per prefetch instruction (multiple of 16)
   int l2pf_gap = 500;      // minimum cycles between two prefetch instructions of a CTA
-  int l2pf_mask = 0x07;    // phases (bit = phase index) during whose loads the producer may prefetch
+  int l2pf_mask = 0x07;    // phases (bit = phase index) during whose loads the producer polls + prefetches; bit 8: poll in all
   unsigned long long* prof = nullptr;  // debug: [CTAs][256][2] globaltimer at (work done, barrier passed) per phase
 };
 size_t mega_lin_bytes(int N, int K);

@@ -989,7 +989,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     if (getenv("MG_MEGA_GATE")) mp.gate = atoi(getenv("MG_MEGA_GATE"));
     if (getenv("MG_MEGA_INFLIGHT")) mp.max_inflight = std::max(1, std::min(5, atoi(getenv("MG_MEGA_INFLIGHT"))));
     if (getenv("MG_MEGA_L2PF")) mp.l2pf = std::max(0, atoi(getenv("MG_MEGA_L2PF"))) * 1024;  // KB per CTA and layer
-    if (getenv("MG_MEGA_L2PF_PIECE")) mp.l2pf_piece = std::max(16, atoi(getenv("MG_MEGA_L2PF_PIECE")) & ~15);
+    if (getenv("MG_MEGA_L2PF_PIECE")) mp.l2pf_piece = std::max(0, atoi(getenv("MG_MEGA_L2PF_PIECE")) & ~15);
     if (getenv("MG_MEGA_L2PF_GAP")) mp.l2pf_gap = std::max(0, atoi(getenv("MG_MEGA_L2PF_GAP")));
     if (getenv("MG_MEGA_L2PF_MASK")) mp.l2pf_mask = (int)strtol(getenv("MG_MEGA_L2PF_MASK"), nullptr, 0);
     if (getenv("MG_MEGA_PROF")) {  // debug: per-phase timestamps of the last step, dumped after the loop
