@@ -330,9 +330,9 @@ def run_ours(args):
             out["roofline"] = {"kernel": "decode_step_kernel (fused persistent decode step: 24 layers + LM head, one "
                                          "launch per generated token)",
                                "bound": "hbm", "achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak,
-                               "traffic": 9.095e9 if (full and args.max_length == 512) else None,
+                               "traffic": 9.133e9 if (full and args.max_length == 512) else None,
                                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the launch at cached "
-                                                 "length 255, ncu --set full, profiles/r1b_ncu_decode_step.txt",
+                                                 "length 255, ncu --set full, profiles/r1c_ncu_decode_step.txt",
                                "peak_source": peak_src,
                                "algorithmic_bytes_per_launch": step_bytes, "ms_per_launch": step_ms,
                                "launches_timed": steps_run * args.steps,
