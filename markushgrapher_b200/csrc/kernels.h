@@ -138,7 +138,7 @@ struct MegaParams {
   const int* lut;
   float* xp;          // [B*H][Mp + 4] softmax numerators (+ their sum) of cross-attention items split over two CTAs
   unsigned* xflag;    // [B*H] epoch flags of xp, zero before the first step
-  float* rs;          // [3][32] RMSNorm row scales published by the qkv / cq / wi phases for their consumers
+  float* rs;          // [3][32] RMSNorm row scales published by the qkv (slot 0) and wi (slot 2) phases for their consumers; slot 1 unused
   unsigned* bar_ctr;  // [2], zero before the first step
   int gate = 0;          // 1: attention K/V streams wait until the consumers enter their phase (measured: no gain)
   int* dbg_host = nullptr;  // host-mapped pinned words for the watchdog's diagnostics (may be null)
