@@ -38,7 +38,12 @@
 
 namespace mg {
 
+#ifdef MK_PF_LANE
+// experiment build (MG_B200_CFLAGS=-DMK_PF_LANE): an 11th warp whose lane 0 is a dedicated L2-prefetch lane, see below
+constexpr int MK_THREADS = 352;
+#else
 constexpr int MK_THREADS = 320;
+#endif
 constexpr int MK_NST = 5;
 constexpr int MK_STAGE = 40960;
 constexpr int MK_WTILE = 32768;  // one (tile, k-block): [hi 128x64 bf16 swizzled][lo ...]
@@ -468,6 +473,45 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
         }
       }
     }
+#ifdef MK_PF_LANE
+  } else if (warp == 10) {
+    // =============================================================================================== L2 prefetch lane
+    // Next-round experiment: the paced prefetch of decision 9 lives in the producer's slot wait and so
+    // realises only ~11 MB per layer.  This lane follows the consumers' phase counter instead: from the moment they
+    // enter layer l (phase 0) until they enter its cross phase it issues p.l2pf bytes of the CTA's coming cross range
+    // (consumption order, like the producer's cursor) as p.l2pf_piece-byte cp.async.bulk.prefetch.L2, one per
+    // p.l2pf_gap cycles, i.e. an even, volume-controlled stream under the qkv / self / o phases.  Build this variant
+    // next to the default library and A/B it with MG_B200_LIB (tools/ab_env.py); set MG_MEGA_L2PF_MASK=0 to switch the
+    // producer's own prefetch off for a clean comparison.
+    if (lane == 0 && p.l2pf > 0 && p.l2pf_piece > 0) {
+      const uint32_t pf_hw = (uint32_t)Mp * 192u;
+      const uint32_t pf_total = min((uint32_t)p.l2pf, (uint32_t)(xh_hi - xh_lo) * pf_hw);
+      for (int l = 0; l < NL && pf_total; ++l) {
+        const uint8_t* ckv = s_layers[l].ckv;
+        const int ph_begin = l * MK_NPH, ph_cross = l * MK_NPH + MK_PH_CROSS;
+        long long t0 = clock64();
+        while (*s_phase < ph_begin) {
+          __nanosleep(200);
+          if (clock64() - t0 > 4000000000LL) mk_die(6, (uint32_t)ph_begin, (uint32_t)*s_phase);
+        }
+        uint32_t cur = 0;
+        long long last = clock64() - p.l2pf_gap;
+        while (cur < pf_total && *s_phase < ph_cross) {
+          const long long now = clock64();
+          if (now - last < (long long)p.l2pf_gap) continue;
+          last = now;
+          const uint32_t j = cur / pf_hw, off = cur - j * pf_hw;
+          int hw;
+          if (x_lone_k && j == 0) hw = xh_hi - 1;
+          else if ((int)j - x_lone_k < 2 * x_whole) hw = 2 * x_first + (int)j - x_lone_k;
+          else hw = xh_lo;
+          const uint32_t n = min(min((uint32_t)p.l2pf_piece, pf_total - cur), pf_hw - off);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(ckv + (size_t)hw * pf_hw + off)), "r"(n) : "memory");
+          cur += n;
+        }
+      }
+    }
+#endif
   } else {
     // =============================================================================================== consumers
     const int ct = threadIdx.x - 64;  // 0..255
