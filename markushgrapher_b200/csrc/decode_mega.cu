@@ -229,7 +229,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
   // attention items are spread over Ga <= G CTAs so that every one of them gets the same count (512 items over 148
   // CTAs would be 3 or 4 each and the phase would run at the pace of 4; over 128 CTAs it is exactly 4 each and HBM,
   // not the SM count, stays the limit)
+#ifdef MK_SELF_ALL
+  // experiment build (-DMK_SELF_ALL): self-attention items over ALL CTAs (3 or 4 each at 512 items / 148 CTAs); the
+  // phase still ends with the 4-item CTAs, but they compete with fewer streams towards its end
+  const int Ga = min(G, n_attn);
+#else
   const int Ga = (n_attn + (n_attn + G - 1) / G - 1) / ((n_attn + G - 1) / G);
+#endif
   const int my_attn = g < Ga ? items_of_cta(n_attn, g, Ga) : 0;
   const int attn_first = g < Ga ? g : n_attn;
   const int Tb = p.Tp >> 5;  // 32-key blocks per (image, head) of the self K cache
