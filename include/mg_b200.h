@@ -86,12 +86,20 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
                      const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length,
                      int64_t* out_ids, int32_t* out_len, int32_t* steps_run);
 
+/* Starts the host->device copy of the NEXT batch's inputs (same HOST pointers that a later mg_generate_host call will
+ * pass, pinned memory; they must stay unchanged until that call) on the model's own copy stream and returns at once,
+ * so the transfer overlaps the decode loop of the batch in flight.  mg_generate_host recognises the staged buffers by
+ * pointer identity and skips its own copies.  Optional: without it mg_generate_host copies inside the call. */
+int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const float* bbox, const float* pixel_values,
+                     const int64_t* attn_mask, int max_length);
+
 /* ---- multi-GPU: image-batch sharding, one process per GPU, one NCCL all-gather of token ids per decode step ----
  * mg_nccl_unique_id: rank 0 obtains a 128-byte NCCL id (host buffer) and ships it to the other ranks by any means
  * (bench.py uses torch.distributed). mg_comm_init: every rank joins. mg_generate_dist: like mg_generate (greedy) on
  * this rank's B_local images; after every step the new token ids of ALL ranks are all-gathered (ncclAllGather of
  * B_local int32 per rank) so every rank fills all_ids (world*B_local, max_length) i64 in global image order and all
- * ranks stop on the same step. B_local must be equal on all ranks. */
+ * ranks stop on the same step. B_local and max_length must be equal on all ranks: the call starts with a handshake
+ * (one 2-int all-gather) and fails on every rank with a message naming the offending rank otherwise. */
 int mg_nccl_unique_id(void* out_128_bytes);
 int mg_comm_init(mg_model* m, int world, int rank, const void* id_128_bytes);
 int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64_t* input_ids, const float* bbox,
@@ -119,9 +127,11 @@ int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kern
  * with CUDA events on the launch stream: total milliseconds, steps executed, and whether the fused persistent
  * decode-step kernel ran (1) or the per-operation kernel chain (0). Host pointers, any may be NULL. */
 int mg_last_decode_loop(mg_model* m, float* loop_ms, int32_t* steps, int32_t* fused);
-/* p50 decode-step latency of the last fused greedy generate: the median, over its 16-step windows, of the mean step
- * time inside a window (CUDA events between windows on the launch stream); 0 if the kernel chain ran. */
+/* Per-step decode latency of the last greedy generate (BASELINE.json "p50 decode lat"): the kernel that ends a decode
+ * step (greedy_select_kernel) stamps %globaltimer on the device; the figures are the median / 99th percentile of the
+ * differences between consecutive steps' stamps, i.e. true per-step latencies, both decode paths. */
 int mg_last_decode_p50(mg_model* m, float* step_p50_ms);
+int mg_last_decode_latency(mg_model* m, float* step_p50_ms, float* step_p99_ms);
 
 /* Measurement hook for bench.py: re-launches the decode cross-attention kernel (the dominant, HBM-bound kernel of
  * the path) over the cross-KV buffers of the preceding mg_generate call, every decoder layer in turn (each

@@ -633,6 +633,13 @@ void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out) {
 // Greedy selection (GenerationMixin._sample :2762-2805): first-max argmax over fp32 logits, finished rows
 // emit pad, EOS bookkeeping, token append, next-step input embedding.  One CTA per image.  The last CTA to
 // finish advances the device step counter and publishes the "all rows finished" flag.
+// Ordering of torch.argmax: the first maximum wins and NaN compares greater than every number (a row of NaN / -inf
+// logits still yields a valid index, never an out-of-range embedding gather).
+__device__ __forceinline__ bool argmax_better(float x, int xi, float best, int bi) {
+  const bool xn = x != x, bn = best != best;
+  if (xn || bn) return xn && (!bn || xi < bi);
+  return x > best || (x == best && xi < bi);
+}
 __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ part_val,
                                                             const int* __restrict__ part_idx, int n_part,
                                                             const float* __restrict__ logits, int V, int64_t ld,
@@ -643,7 +650,8 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
                                                             float* __restrict__ x_next, float* __restrict__ logits_dump,
                                                             int64_t dump_bs, int64_t dump_ss,
                                                             const int64_t* __restrict__ forced, int forced_ld,
-                                                            int* __restrict__ step_tok) {
+                                                            int* __restrict__ step_tok,
+                                                            unsigned long long* __restrict__ step_ts) {
   const int b = blockIdx.x;
   griddep_launch();
   griddep_wait();
@@ -655,7 +663,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
     for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
       const float x = part_val[(int64_t)b * n_part + i];
       const int xi = part_idx[(int64_t)b * n_part + i];
-      if (x > best || (x == best && xi < bi)) {
+      if (argmax_better(x, xi, best, bi)) {
         best = x;
         bi = xi;
       }
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
       const float x = lg[i];
       if (logits_dump) logits_dump[(int64_t)b * dump_bs + (int64_t)step * dump_ss + i] = x;
-      if (x > best || (x == best && i < bi)) {
+      if (argmax_better(x, i, best, bi)) {
         best = x;
         bi = i;
       }
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ob > best || (ob == best && oi < bi)) {
+    if (argmax_better(ob, oi, best, bi)) {
       best = ob;
       bi = oi;
     }
@@ -692,10 +700,11 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w)
-      if (sb[w] > best || (sb[w] == best && si[w] < bi)) {
+      if (argmax_better(sb[w], si[w], best, bi)) {
         best = sb[w];
         bi = si[w];
       }
+    bi = min(max(bi, 0), V - 1);
     const int fin = finished[b];
     int tok = fin ? pad : bi;
     out_ids[(int64_t)b * out_ld + step + 1] = tok;
@@ -721,6 +730,11 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
     if (t == (int)gridDim.x - 1) {
       *ticket = 0;
       *step_ptr = step + 1;
+      if (step_ts) {  // %globaltimer at the end of every decode step: true per-step latencies (mg_last_decode_p50)
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        step_ts[step] = now;
+      }
     }
   }
 }
@@ -729,20 +743,21 @@ void launch_greedy_select(cudaStream_t st, const float* part_val, const int* par
                           int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
-                          int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok) {
+                          int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok,
+                          unsigned long long* step_ts) {
   launch_pdl(greedy_select_kernel, dim3(B), dim3(256), (size_t)0, st, part_val, part_idx, n_part, logits, V, ld, emb, D,
              eos, pad, out_ids, out_ld,
              finished, step_ptr, n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss, forced, forced_ld,
-             step_tok);
+             step_tok, step_ts);
 }
 
 // decode state reset: ids[:,0] = start token, x = emb[start], finished = 0, step = 0
-__global__ void decode_init_kernel(const float* __restrict__ emb, int D, int start, int B, int64_t* out_ids, int out_ld,
-                                   int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
+__global__ void decode_init_kernel(const float* __restrict__ emb, int D, int start, int pad, int B, int64_t* out_ids,
+                                   int out_ld, int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
                                    const int64_t* __restrict__ forced, int forced_ld) {
   const int b = blockIdx.x;
   if (forced) start = (int)forced[(int64_t)b * forced_ld];
-  for (int i = threadIdx.x; i < out_ld; i += blockDim.x) out_ids[(int64_t)b * out_ld + i] = (i == 0) ? start : 0;
+  for (int i = threadIdx.x; i < out_ld; i += blockDim.x) out_ids[(int64_t)b * out_ld + i] = (i == 0) ? start : pad;
   for (int c = threadIdx.x; c < D; c += blockDim.x) x[(int64_t)b * D + c] = emb[(int64_t)start * D + c];
   if (threadIdx.x == 0) {
     finished[b] = 0;
@@ -753,10 +768,10 @@ __global__ void decode_init_kernel(const float* __restrict__ emb, int D, int sta
     }
   }
 }
-void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int B, int64_t* out_ids, int out_ld,
-                        int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
+void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int pad, int B, int64_t* out_ids,
+                        int out_ld, int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
                         const int64_t* forced, int forced_ld) {
-  decode_init_kernel<<<B, 256, 0, st>>>(emb, D, start, B, out_ids, out_ld, finished, step_ptr, n_unfinished, ticket, x,
+  decode_init_kernel<<<B, 256, 0, st>>>(emb, D, start, pad, B, out_ids, out_ld, finished, step_ptr, n_unfinished, ticket, x,
                                         forced, forced_ld);
   MG_CHECK_CUDA(cudaGetLastError());
 }

@@ -53,11 +53,12 @@ void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
 void launch_greedy_select(cudaStream_t st, const float* part_val, const int* part_idx, int n_part, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
-                          int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok);
+                          int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok,
+                          unsigned long long* step_ts = nullptr);
 void launch_scatter_step(cudaStream_t st, const int* gathered, int n_rows, int col, int ld, int eos, int64_t* all_ids,
                          int* gfinished, int* g_unfinished);
-void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int B, int64_t* out_ids, int out_ld,
-                        int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
+void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int pad, int B, int64_t* out_ids,
+                        int out_ld, int* finished, int* step_ptr, int* n_unfinished, int* ticket, float* x,
                         const int64_t* forced, int forced_ld);
 
 void launch_out_len(cudaStream_t st, const int64_t* ids, int B, int ld, int ncols, int eos, int* len);

@@ -181,8 +181,7 @@ struct mg_model {
   int last_loop_steps = 0;
   int last_fused = 0;         // 1 if the last greedy generate used the fused persistent decode-step kernel
   cudaEvent_t ev_loop[2] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> ev_win;  // one event per 16-step window of the fused decode loop (p50 step latency)
-  float last_step_p50_ms = 0.f;
+  float last_step_p50_ms = 0.f, last_step_p99_ms = 0.f;  // per-step latencies from the %globaltimer stamp of every step
   int64_t last_launches = 0;
   int* pinned_flag = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -194,6 +193,7 @@ struct mg_model {
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
   int64_t* dist_all_ids = nullptr;  // (world*B, max_length) on every rank, set per call
+  int* dist_chk = nullptr;          // [2 + 2*world] shard-shape handshake of mg_generate_dist
   // buffers of the last generate call (valid until the next encode/generate), for mg_profile_cross_attn
   std::vector<float*> prof_ckt, prof_cv;
   std::vector<uint8_t*> prof_ckv;
@@ -212,6 +212,11 @@ struct mg_model {
     persist.release();
     scratch.release();
     if (pinned_flag) cudaFreeHost(pinned_flag);
+    for (auto& hs : stage) {
+      if (hs.buf) cudaFree(hs.buf);
+      if (hs.ready) cudaEventDestroy(hs.ready);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (aux_stream) cudaStreamDestroy(aux_stream);
     for (auto& e : lane_ev)
@@ -220,8 +225,6 @@ struct mg_model {
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     for (auto& e : ev_loop)
-      if (e) cudaEventDestroy(e);
-    for (auto& e : ev_win)
       if (e) cudaEventDestroy(e);
   }
 
@@ -291,6 +294,50 @@ struct mg_model {
     MG_CHECK_CUDA(cudaMemcpyAsync(p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, st));
     MG_CHECK_CUDA(cudaStreamSynchronize(st));  // v is a temporary
     return p;
+  }
+
+  // host-entry staging (mg_generate_host / mg_prefetch_host): two device slots owned by the model, so that the
+  // inputs of batch i+1 can travel host->device on the copy stream while batch i is decoding
+  struct HostStage {
+    void* buf = nullptr;
+    size_t cap = 0;
+    const void *k_ids = nullptr, *k_box = nullptr, *k_px = nullptr, *k_mask = nullptr;  // host pointers staged here
+    int B = 0, Lt = 0;
+    bool valid = false;
+    cudaEvent_t ready = nullptr;
+    int64_t *d_ids = nullptr, *d_mask = nullptr, *d_out = nullptr;
+    float *d_box = nullptr, *d_px = nullptr;
+  };
+  HostStage stage[2];
+  int stage_busy = -1;  // slot the running / last generate reads from
+  cudaStream_t copy_stream = nullptr;
+  // copies one batch of host inputs into slot `s` on stream `cs` (max_length sizes the ids-out buffer)
+  void stage_inputs(HostStage& s, cudaStream_t cs, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
+                    const int64_t* mask, int out_cols) {
+    const size_t n_ids = (size_t)B * Lt, n_px = (size_t)B * 3 * cfg.image_size * cfg.image_size;
+    const size_t need = rup(n_ids * 8, 256) * 2 + rup(n_ids * 16, 256) + rup(n_px * 4, 256) + rup((size_t)B * out_cols * 8, 256);
+    if (need > s.cap) {
+      if (s.buf) MG_CHECK_CUDA(cudaFree(s.buf));
+      s.buf = nullptr;
+      s.cap = 0;
+      MG_CHECK_CUDA(cudaMalloc(&s.buf, need));
+      s.cap = need;
+    }
+    if (!s.ready) MG_CHECK_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+    char* p = static_cast<char*>(s.buf);
+    s.d_ids = reinterpret_cast<int64_t*>(p); p += rup(n_ids * 8, 256);
+    s.d_mask = reinterpret_cast<int64_t*>(p); p += rup(n_ids * 8, 256);
+    s.d_box = reinterpret_cast<float*>(p); p += rup(n_ids * 16, 256);
+    s.d_px = reinterpret_cast<float*>(p); p += rup(n_px * 4, 256);
+    s.d_out = reinterpret_cast<int64_t*>(p);
+    MG_CHECK_CUDA(cudaMemcpyAsync(s.d_ids, ids, n_ids * 8, cudaMemcpyHostToDevice, cs));
+    if (mask) MG_CHECK_CUDA(cudaMemcpyAsync(s.d_mask, mask, n_ids * 8, cudaMemcpyHostToDevice, cs));
+    MG_CHECK_CUDA(cudaMemcpyAsync(s.d_box, bbox, n_ids * 16, cudaMemcpyHostToDevice, cs));
+    MG_CHECK_CUDA(cudaMemcpyAsync(s.d_px, px, n_px * 4, cudaMemcpyHostToDevice, cs));
+    MG_CHECK_CUDA(cudaEventRecord(s.ready, cs));
+    s.k_ids = ids; s.k_box = bbox; s.k_px = px; s.k_mask = mask;
+    s.B = B; s.Lt = Lt;
+    s.valid = true;
   }
 
   int64_t* ids_buf = nullptr;
@@ -901,6 +948,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   int* gctr = a.get<int>(8);  // [3] = global n_unfinished (multi-GPU)
   const bool dist = comm != nullptr && dist_all_ids != nullptr && forced == nullptr;
   int* step_tok = a.get<int>(B);
+  unsigned long long* step_ts = a.get<unsigned long long>(max_length);  // %globaltimer at the end of every step
   int* gathered = a.get<int>((int64_t)world * B);
   int* gfinished = a.get<int>((int64_t)world * B);
 
@@ -947,7 +995,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   int64_t* ids_dev = out_ids;
   for (int i = 0; i < nlanes; ++i) {
     Lane& L = lanes[i];
-    launch_decode_init(st, shared, d, c.decoder_start_token_id, L.bn, ids_dev + (int64_t)L.b0 * max_length, max_length,
+    launch_decode_init(st, shared, d, c.decoder_start_token_id, c.pad_token_id, L.bn, ids_dev + (int64_t)L.b0 * max_length, max_length,
                        finished + L.b0, L.ctr, L.ctr + 1, L.ctr + 2, x + (int64_t)L.b0 * d,
                        forced ? forced + (int64_t)L.b0 * forced_ld : nullptr, forced_ld);
     ++launches;
@@ -1004,7 +1052,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       launch_decode_step(ls, mp, mega_ctas);
       launch_greedy_select(ls, part_val, part_idx, n_part, logits, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
                            ids_dev, max_length, finished, Ln.ctr, Ln.ctr + 1, Ln.ctr + 2, x,
-                           step_logits, (int64_t)(max_length - 1) * V, V, forced, forced_ld, step_tok);
+                           step_logits, (int64_t)(max_length - 1) * V, V, forced, forced_ld, step_tok, step_ts);
       launches += 2;
       return;
     }
@@ -1049,7 +1097,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
                          x + (int64_t)b0 * d,
                          step_logits ? step_logits + (int64_t)b0 * (max_length - 1) * V : nullptr,
                          (int64_t)(max_length - 1) * V, V, forced ? forced + (int64_t)b0 * forced_ld : nullptr,
-                         forced_ld, step_tok + b0);
+                         forced_ld, step_tok + b0, b0 == 0 ? step_ts : nullptr);
     launches += 1;
   };
   // one step of every lane; in multi-GPU mode followed by the exchange of the step's token ids
@@ -1085,17 +1133,6 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     // two launches per token: nothing to capture, the host simply runs ahead of the GPU
     pinned_flag[0] = pinned_flag[1] = B;
     bool stop = false;
-    size_t n_win = 0;
-    std::vector<int> win_steps;
-    auto mark = [&]() {
-      if (n_win == ev_win.size()) {
-        cudaEvent_t e;
-        MG_CHECK_CUDA(cudaEventCreate(&e));
-        ev_win.push_back(e);
-      }
-      MG_CHECK_CUDA(cudaEventRecord(ev_win[n_win++], st));
-    };
-    mark();
     try {
     while (done_steps < total_steps && !stop) {
       const int n = std::min(16, total_steps - done_steps);
@@ -1103,8 +1140,6 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
         one_step(lanes[0]);
         if (dist) exchange(done_steps + i + 1);
       }
-      mark();
-      win_steps.push_back(n);
       done_steps += n;
       MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));  // poll the "all finished" counter one window late
       if (pinned_flag[0] == 0) stop = true;
@@ -1112,16 +1147,6 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
     }
     MG_CHECK_CUDA(cudaStreamSynchronize(st));
-    {  // median over the windows of the mean step latency inside a window
-      std::vector<float> per;
-      for (size_t w = 0; w + 1 < n_win; ++w) {
-        float ms = 0.f;
-        MG_CHECK_CUDA(cudaEventElapsedTime(&ms, ev_win[w], ev_win[w + 1]));
-        per.push_back(ms / (float)win_steps[w]);
-      }
-      std::sort(per.begin(), per.end());
-      last_step_p50_ms = per.empty() ? 0.f : per[per.size() / 2];
-    }
     } catch (const Error& e) {
       if (pinned_flag[8] != 0)  // the fused kernel's watchdog fired: say where
         throw Error(e.code, std::string(e.what()) + " [decode_step_kernel watchdog: code " + std::to_string(pinned_flag[8]) +
@@ -1183,6 +1208,15 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   MG_CHECK_CUDA(cudaEventElapsedTime(&last_loop_ms, ev_loop[0], ev_loop[1]));
   last_loop_steps = done_steps;
   last_fused = use_mega ? 1 : 0;
+  {  // true per-step latencies: differences of the device-side end-of-step stamps (greedy_select_kernel)
+    std::vector<unsigned long long> ts((size_t)done_steps);
+    MG_CHECK_CUDA(cudaMemcpy(ts.data(), step_ts, sizeof(unsigned long long) * ts.size(), cudaMemcpyDeviceToHost));
+    std::vector<float> per;
+    for (size_t i = 1; i < ts.size(); ++i) per.push_back((float)((double)(ts[i] - ts[i - 1]) * 1e-6));
+    std::sort(per.begin(), per.end());
+    last_step_p50_ms = per.empty() ? 0.f : per[per.size() / 2];
+    last_step_p99_ms = per.empty() ? 0.f : per[std::min(per.size() - 1, (size_t)(per.size() * 0.99))];
+  }
   if (use_mega && mp.prof) {
     std::vector<unsigned long long> h((size_t)mega_ctas * 1024);
     MG_CHECK_CUDA(cudaMemcpy(h.data(), mp.prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1451,6 +1485,22 @@ int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64
   MG_API_BEGIN
   MG_REQUIRE(m && m->comm, "mg_comm_init has not been called");
   MG_REQUIRE(all_ids, "null argument");
+  {  // every rank must bring the same shard size and length: unequal counts would hang or corrupt the all-gather
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (!m->dist_chk) m->dist_chk = m->own<int>(2 + 2 * 64);
+    MG_REQUIRE(m->world <= 64, "at most 64 ranks");
+    const int mine[2] = {B_local, max_length};
+    MG_CHECK_CUDA(cudaMemcpyAsync(m->dist_chk, mine, sizeof(mine), cudaMemcpyHostToDevice, cs));
+    MG_CHECK_NCCL(nccl_api().AllGather(m->dist_chk, m->dist_chk + 2, 2, ncclInt32, m->comm, cs));
+    std::vector<int> all((size_t)2 * m->world);
+    MG_CHECK_CUDA(cudaMemcpyAsync(all.data(), m->dist_chk + 2, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, cs));
+    MG_CHECK_CUDA(cudaStreamSynchronize(cs));
+    for (int r = 0; r < m->world; ++r)
+      MG_REQUIRE(all[2 * r] == B_local && all[2 * r + 1] == max_length,
+                 "mg_generate_dist: rank " + std::to_string(r) + " brought B_local=" + std::to_string(all[2 * r]) +
+                     " max_length=" + std::to_string(all[2 * r + 1]) + ", this rank B_local=" + std::to_string(B_local) +
+                     " max_length=" + std::to_string(max_length) + " (pad the shards to one size)");
+  }
   int64_t* local = m->persist_ids((int64_t)B_local * max_length);
   m->dist_all_ids = all_ids;
   int rc = mg_generate(m, stream, B_local, Lt, input_ids, bbox, pixel_values, attn_mask, 1, max_length, local, nullptr,
@@ -1494,27 +1544,25 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
     st = m->own_stream;
   }
   const mg_config& c = m->cfg;
-  // staging buffers live in their own small allocations (kept across calls)
-  static thread_local void* stage = nullptr;
-  static thread_local size_t stage_cap = 0;
-  const size_t n_ids = (size_t)B * Lt, n_px = (size_t)B * 3 * c.image_size * c.image_size;
-  const size_t need = rup(n_ids * 8, 256) * 2 + rup(n_ids * 16, 256) + rup(n_px * 4, 256) + rup((size_t)B * max_length * 8, 256);
-  if (need > stage_cap) {
-    if (stage) cudaFree(stage);
-    MG_CHECK_CUDA(cudaMalloc(&stage, need));
-    stage_cap = need;
+  // a slot already filled by mg_prefetch_host from these very host buffers is used as is; otherwise stage now
+  int slot = -1;
+  for (int i = 0; i < 2; ++i) {
+    const mg_model::HostStage& s = m->stage[i];
+    if (s.valid && s.k_ids == input_ids && s.k_box == bbox && s.k_px == pixel_values && s.k_mask == attn_mask &&
+        s.B == B && s.Lt == Lt && s.cap >= (size_t)((char*)s.d_out - (char*)s.buf) + (size_t)B * max_length * 8)
+      slot = i;
   }
-  char* p = static_cast<char*>(stage);
-  int64_t* d_ids = reinterpret_cast<int64_t*>(p); p += rup(n_ids * 8, 256);
-  int64_t* d_mask = reinterpret_cast<int64_t*>(p); p += rup(n_ids * 8, 256);
-  float* d_box = reinterpret_cast<float*>(p); p += rup(n_ids * 16, 256);
-  float* d_px = reinterpret_cast<float*>(p); p += rup(n_px * 4, 256);
-  int64_t* d_out = reinterpret_cast<int64_t*>(p);
-  MG_CHECK_CUDA(cudaMemcpyAsync(d_ids, input_ids, n_ids * 8, cudaMemcpyHostToDevice, st));
-  if (attn_mask) MG_CHECK_CUDA(cudaMemcpyAsync(d_mask, attn_mask, n_ids * 8, cudaMemcpyHostToDevice, st));
-  MG_CHECK_CUDA(cudaMemcpyAsync(d_box, bbox, n_ids * 16, cudaMemcpyHostToDevice, st));
-  MG_CHECK_CUDA(cudaMemcpyAsync(d_px, pixel_values, n_px * 4, cudaMemcpyHostToDevice, st));
-  int rc = mg_generate(m, st, B, Lt, d_ids, d_box, d_px, attn_mask ? d_mask : nullptr, num_beams, max_length, d_out,
+  if (slot >= 0) {
+    MG_CHECK_CUDA(cudaStreamWaitEvent(st, m->stage[slot].ready, 0));
+  } else {
+    slot = m->stage_busy == 0 ? 1 : 0;
+    m->stage_inputs(m->stage[slot], st, B, Lt, input_ids, bbox, pixel_values, attn_mask, max_length);
+  }
+  mg_model::HostStage& S = m->stage[slot];
+  m->stage_busy = slot;
+  S.valid = false;  // consumed: a later call with the same host pointers copies again (the caller may have refilled them)
+  int64_t* d_out = S.d_out;
+  int rc = mg_generate(m, st, B, Lt, S.d_ids, S.d_box, S.d_px, attn_mask ? S.d_mask : nullptr, num_beams, max_length, d_out,
                        nullptr, nullptr, steps_run);
   if (rc != 0) return rc;
   MG_CHECK_CUDA(cudaMemcpyAsync(out_ids, d_out, (size_t)B * max_length * 8, cudaMemcpyDeviceToHost, st));
@@ -1530,6 +1578,18 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
       out_len[b] = len;
     }
   }
+  MG_API_END
+}
+
+int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const float* bbox, const float* pixel_values,
+                     const int64_t* attn_mask, int max_length) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values, "null argument");
+  MG_REQUIRE(m->finalized, "mg_finalize has not been called");
+  MG_REQUIRE(B > 0 && Lt > 0 && max_length >= 2, "bad sizes");
+  if (!m->copy_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  const int slot = m->stage_busy == 0 ? 1 : 0;  // never the slot the running / last generate call reads
+  m->stage_inputs(m->stage[slot], m->copy_stream, B, Lt, input_ids, bbox, pixel_values, attn_mask, max_length);
   MG_API_END
 }
 
@@ -1576,6 +1636,14 @@ int mg_last_decode_p50(mg_model* m, float* step_p50_ms) {
   MG_API_BEGIN
   MG_REQUIRE(m, "null model");
   if (step_p50_ms) *step_p50_ms = m->last_step_p50_ms;
+  MG_API_END
+}
+
+int mg_last_decode_latency(mg_model* m, float* step_p50_ms, float* step_p99_ms) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (step_p50_ms) *step_p50_ms = m->last_step_p50_ms;
+  if (step_p99_ms) *step_p99_ms = m->last_step_p99_ms;
   MG_API_END
 }
 

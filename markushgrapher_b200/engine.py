@@ -97,6 +97,8 @@ class MGEngine:
         L.mg_last_stats.argtypes = [ctypes.c_void_p] * 4
         L.mg_last_decode_loop.argtypes = [ctypes.c_void_p] * 4
         L.mg_last_decode_p50.argtypes = [ctypes.c_void_p] * 2
+        L.mg_last_decode_latency.argtypes = [ctypes.c_void_p] * 3
+        L.mg_prefetch_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
         L.mg_destroy.argtypes = [ctypes.c_void_p]
         L.mg_destroy.restype = None
         self.n_patches = (cfg.image_size // cfg.patch_size) ** 2
@@ -178,6 +180,18 @@ class MGEngine:
             out = out[:, : _stop_column(out, lens, max_length)]
         return out
 
+    def prefetch_host(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512):
+        """start the H2D copy of the NEXT batch (pinned HOST tensors, the very objects later passed to generate_host)
+        on the library's copy stream; returns immediately so the copy overlaps the decode of the batch in flight"""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, "cpu")
+        for t, o in ((ids, input_ids), (box, bbox), (px, pixel_values)):
+            if t.data_ptr() != o.data_ptr():
+                raise _lib.MgError("prefetch_host needs contiguous int64 / float32 host tensors (no conversion copy)")
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().mg_prefetch_host(self._h, B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px), _lib.ptr(am),
+                                             int(max_length))
+        _lib.check(rc, "mg_prefetch_host")
+
     # ------------------------------------------------------------------ multi-GPU (one process per GPU)
     def comm_init_from_torch(self, group=None):
         """join an NCCL communicator owned by the library; the 128-byte id travels over torch.distributed"""
@@ -238,9 +252,11 @@ class MGEngine:
         ms, n, f = ctypes.c_float(0), ctypes.c_int32(0), ctypes.c_int32(0)
         _lib.check(_lib.lib().mg_last_decode_loop(self._h, ctypes.addressof(ms), ctypes.addressof(n),
                                                   ctypes.addressof(f)), "mg_last_decode_loop")
-        p50 = ctypes.c_float(0)
-        _lib.check(_lib.lib().mg_last_decode_p50(self._h, ctypes.addressof(p50)), "mg_last_decode_p50")
-        return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value), "step_p50_ms": p50.value}
+        p50, p99 = ctypes.c_float(0), ctypes.c_float(0)
+        _lib.check(_lib.lib().mg_last_decode_latency(self._h, ctypes.addressof(p50), ctypes.addressof(p99)),
+                   "mg_last_decode_latency")
+        return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value), "step_p50_ms": p50.value,
+                "step_p99_ms": p99.value}
 
     def last_stats(self):
         e, d, k = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int64(0)

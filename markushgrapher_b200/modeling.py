@@ -104,9 +104,9 @@ class MarkushgrapherForConditionalGeneration(nn.Module):
     def device(self) -> torch.device:
         return next(self.parameters()).device
 
-    @property
-    def module(self):  # reference utils_evaluation.py:269 uses model.module when DDP-wrapped
-        return self
+    # NB: no `.module` attribute here. The reference tests `hasattr(model, "module")` (utils_evaluation.py:269) to detect
+    # a DDP wrapper and then decodes greedily; on the bare model it must take the predict.yaml branch
+    # (`beam_search: True` -> generate(num_beams=5), :278-285). A DDP wrapper supplies its own `.module`.
 
     @classmethod
     def from_pretrained(cls, path: str, config: Optional[MarkushgrapherConfig] = None, **kw):
@@ -126,8 +126,9 @@ class MarkushgrapherForConditionalGeneration(nn.Module):
         if sd is None:
             raise FileNotFoundError(f"no weights (model.safetensors / pytorch_model.bin) under {path}")
         missing = model.safe_load(model, sd)
-        if missing:
-            warnings.warn(f"{len(missing)} parameters not found in checkpoint, e.g. {missing[:3]}")
+        if missing:  # (a tied head absent from the file is aliased to shared.weight inside safe_load)
+            raise KeyError(f"{len(missing)} parameters of the path are missing from the checkpoint under {path} "
+                           f"(or have another shape), e.g. {missing[:5]}")
         return model
 
     def save_pretrained(self, path: str) -> None:
@@ -150,6 +151,11 @@ class MarkushgrapherForConditionalGeneration(nn.Module):
         for a, b in aliases.items():
             if a in clean and b not in clean:
                 clean[b] = clean[a]
+        # tied head: HF checkpoints saved with tie_word_embeddings=True carry no lm_head.weight (safetensors drops the
+        # duplicate), the head IS the embedding matrix (TF/models/udop/modeling_udop.py:1587-1590)
+        if "lm_head.weight" in own and "lm_head.weight" not in clean and "shared.weight" in clean:
+            if getattr(self.config, "tie_word_embeddings", True):
+                clean["lm_head.weight"] = clean["shared.weight"]
         missing = []
         with torch.no_grad():
             for k, p in own.items():

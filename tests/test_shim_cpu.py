@@ -42,10 +42,36 @@ def test_model_object_contract(tmp_path):
     for k, v in m.state_dict().items():
         assert torch.equal(v, m2.state_dict()[k]), k
     assert m.init_molscribe_weights() is False     # checkpoint not on disk here -> warns, keeps weights
-    assert m.device.type == "cpu" and m.module is m
+    assert m.device.type == "cpu"
+    # the reference detects a DDP wrapper with hasattr(model, "module") (utils_evaluation.py:269) and then decodes
+    # greedily; the bare model must NOT look wrapped or predict.yaml's beam search is silently downgraded
+    assert not hasattr(m, "module")
     with pytest.raises(RuntimeError):              # no CPU fallback
         m.generate(input_ids=torch.zeros(1, 4, dtype=torch.long), bbox=torch.zeros(1, 4, 4),
                    pixel_values=torch.zeros(1, 3, 64, 64))
+
+
+def test_tied_head_checkpoint_and_missing_weights(tmp_path):
+    """a checkpoint saved with tie_word_embeddings=True has no lm_head.weight: the head aliases shared.weight;
+    anything else missing is an error, not a warning"""
+    from markushgrapher_b200.modeling import MarkushgrapherForConditionalGeneration as M
+
+    cfg = small_cfg()
+    m = M(cfg)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    del sd["lm_head.weight"]
+    m.config.save_pretrained(str(tmp_path))
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    m2 = M.from_pretrained(str(tmp_path))
+    assert torch.equal(m2.state_dict()["lm_head.weight"], sd["shared.weight"])
+    untied = small_cfg()
+    untied.tie_word_embeddings = False
+    with pytest.raises(KeyError):
+        M.from_pretrained(str(tmp_path), config=untied)
+    del sd["decoder.final_layer_norm.weight"]
+    torch.save(sd, str(tmp_path / "pytorch_model.bin"))
+    with pytest.raises(KeyError):
+        M.from_pretrained(str(tmp_path))
 
 
 def test_swin_timm_name_conversion():
