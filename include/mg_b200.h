@@ -120,6 +120,8 @@ int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* i
  *   MG_MEGA_L2PF=<KB> bytes of the coming cross-attention phase each CTA of the fused kernel prefetches into L2
  *                    (default 384, 0 = off; timing only, results identical). */
 
+/* kernels this model has launched since mg_finalize (every entry point counts its own launches) */
+int mg_launch_count(mg_model* m, int64_t* kernels_launched);
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched);
 

@@ -1656,6 +1656,13 @@ int mg_last_decode_loop(mg_model* m, float* loop_ms, int32_t* steps, int32_t* fu
   MG_API_END
 }
 
+int mg_launch_count(mg_model* m, int64_t* kernels_launched) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && kernels_launched, "null argument");
+  *kernels_launched = m->launches;
+  MG_API_END
+}
+
 int mg_last_stats(mg_model* m, float* encode_ms, float* decode_ms, int64_t* kernels_launched) {
   MG_API_BEGIN
   MG_REQUIRE(m, "null model");

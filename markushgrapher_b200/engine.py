@@ -258,6 +258,13 @@ class MGEngine:
         return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value), "step_p50_ms": p50.value,
                 "step_p99_ms": p99.value}
 
+    def launch_count(self) -> int:
+        k = ctypes.c_int64(0)
+        L = _lib.lib()
+        L.mg_launch_count.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _lib.check(L.mg_launch_count(self._h, ctypes.addressof(k)), "mg_launch_count")
+        return k.value
+
     def last_stats(self):
         e, d, k = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int64(0)
         _lib.check(_lib.lib().mg_last_stats(self._h, ctypes.addressof(e), ctypes.addressof(d), ctypes.addressof(k)),
