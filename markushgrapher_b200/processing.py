@@ -7,6 +7,7 @@ packing.py."""
 from __future__ import annotations
 
 import os
+import re
 from typing import List, Optional
 
 import numpy as np
@@ -66,6 +67,62 @@ def collate_cells(image, cells, tokenizer, question: str, normalize_bbox: bool =
     if normalize_bbox:
         boxes = [[b[0] / w, b[1] / h, b[2] / w, b[3] / h] for b in boxes]
     return image, f"Question Answering. {question}", words, boxes
+
+
+# ------------------------------------------------------------------------------------------------ ChemicalOCR hand-off
+_LOC = re.compile(r"<loc_(\d+)>")
+_LOC4 = re.compile(r"(?:<loc_\d+>){4}")
+_NUM_LINE = re.compile(r"^(?:\d+>)*(\d+)>(\d+)>(\d+)>(\d+)>(.+)$")
+
+
+def clean_ocr_text(text: str, start_tag: str = "<ocr>", end_tag: Optional[str] = "</ocr>") -> str:
+    """keep what lies between the first `start_tag` and the first `end_tag`, tags included (the VLM may chat before and
+    after its answer) -- reference ocr/chemical_ocr.py:202-223"""
+    i = text.find(start_tag)
+    if i >= 0:
+        text = text[i:]
+    if end_tag:
+        j = text.find(end_tag)
+        if j >= 0:  # (the reference's `.*?$` stops in front of a final newline, which therefore survives)
+            text = text[: j + len(end_tag)] + ("\n" if text.endswith("\n") else "")
+    return text
+
+
+def parse_ocr_string(ocr_string: str):
+    """ChemicalOCR's generated string -> (words, boxes normalised by the 500-unit page), reference
+    ocr/chemical_ocr.py:165-199.  Two line formats: legacy `<loc_x1><loc_y1><loc_x2><loc_y2>text` (after an optional
+    leading page box `<loc_0><loc_0><loc_500><loc_500>`), and `x1>y1>x2>y2>text` with any number of leading `N>`
+    fields skipped (the page box on the first line).  Lines without text or with fewer than four numbers are dropped;
+    the LAST four numbers of a legacy line are its box."""
+    body = ocr_string.replace("<ocr>", "").replace("</ocr>", "").strip()
+    words, boxes = [], []
+    if "<loc_" in body:
+        page = "<loc_0><loc_0><loc_500><loc_500>"
+        if body.startswith(page):
+            body = body[len(page):].strip()
+        for line in body.splitlines():
+            nums = [int(n) for n in _LOC.findall(line)]
+            text = _LOC4.sub("", line).strip()
+            if len(nums) >= 4 and text:
+                words.append(text)
+                boxes.append([v / 500 for v in nums[-4:]])
+    else:
+        for line in body.splitlines():
+            m = _NUM_LINE.match(line.strip())
+            if not m:
+                continue
+            text = m.group(5).strip()
+            if text:
+                words.append(text)
+                boxes.append([int(m.group(k)) / 500 for k in (1, 2, 3, 4)])
+    return words, boxes
+
+
+def cells_from_ocr_string(output_text: str):
+    """one generated string -> the OCR cells [{"bbox", "text"}] the reference stores per image
+    (ocr/chemical_ocr.py:447-455); feed them to MarkushgrapherProcessor.from_cells"""
+    words, boxes = parse_ocr_string(clean_ocr_text(output_text))
+    return [{"bbox": b, "text": w} for w, b in zip(words, boxes)]
 
 
 class MarkushgrapherImageProcessor:
