@@ -95,15 +95,18 @@ int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const
 
 /* ---- multi-GPU: image-batch sharding, one process per GPU, one NCCL all-gather of token ids per decode step ----
  * mg_nccl_unique_id: rank 0 obtains a 128-byte NCCL id (host buffer) and ships it to the other ranks by any means
- * (bench.py uses torch.distributed). mg_comm_init: every rank joins. mg_generate_dist: like mg_generate (greedy) on
- * this rank's B_local images; after every step the new token ids of ALL ranks are all-gathered (ncclAllGather of
- * B_local int32 per rank) so every rank fills all_ids (world*B_local, max_length) i64 in global image order and all
- * ranks stop on the same step. B_local and max_length must be equal on all ranks: the call starts with a handshake
+ * (bench.py uses torch.distributed). mg_comm_init: every rank joins. mg_generate_dist: like mg_generate on this rank's
+ * B_local images; after every step the new token ids of ALL ranks are all-gathered (ncclAllGather of B_local int32 per
+ * rank) so every rank fills all_ids (world*B_local, max_length) i64 in global image order and all ranks stop on the
+ * same step.  num_beams > 1 (the reference's predict.yaml default decodes with beams): the beams of an image stay on
+ * its GPU; the per-step all-gather carries the token of every image's best running beam plus the rank's "done" flag
+ * (B_local + 1 int32), ranks whose search is over stay frozen until all are, and one final all-gather replaces the
+ * provisional columns of all_ids with the finished sequences. B_local and max_length must be equal on all ranks: the call starts with a handshake
  * (one 2-int all-gather) and fails on every rank with a message naming the offending rank otherwise. */
 int mg_nccl_unique_id(void* out_128_bytes);
 int mg_comm_init(mg_model* m, int world, int rank, const void* id_128_bytes);
 int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64_t* input_ids, const float* bbox,
-                     const float* pixel_values, const int64_t* attn_mask, int max_length, int64_t* all_ids,
+                     const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length, int64_t* all_ids,
                      int32_t* steps_run);
 
 /* Teacher-forced logits, the reference's `model(**batch).logits` with decoder_input_ids = shift_right(labels):

@@ -341,6 +341,215 @@ void launch_beam_cross_attn(cudaStream_t st, const float* q, int B, int nq, int 
   launch_pdl(beam_cross_attn_kernel, grid, dim3(288), smem, st, q, kt, v, mask, Mp, H, D, nq, ctx);
 }
 
+// kv24 variant (decode.cu: 16-bit + 8-bit planes, 3 bytes per element, the format the greedy paths stream): one CTA
+// per (head, IMAGE), the image's block streamed ONCE for its nq beams -- per generated token a beam-4 decode moves
+// 3/16 of the bytes of the reference's nb-times-repeated fp32 encoder K/V.  Scores: thread = pair of adjacent keys.
+__global__ void __launch_bounds__(288) beam_cross_attn24_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kv,
+                                                                const int* __restrict__ mask, int Mp, int H, int D,
+                                                                int nq, float* __restrict__ ctx) {
+  constexpr int HD = 64;
+  extern __shared__ __align__(128) uint8_t smc[];
+  uint8_t* ring = smc;
+  float* sc = reinterpret_cast<float*>(smc + BC_NST * BC_STAGE_BYTES);  // [nq][Mp]
+  float* sq = sc + (int64_t)nq * Mp;                                    // [nq][64]
+  float* sred = sq + nq * HD;                                           // [16*64]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sred + 16 * HD);
+  uint64_t* empty_bar = full_bar + BC_NST;
+  float* s_b = reinterpret_cast<float*>(empty_bar + BC_NST);            // [8 warps]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n = (int64_t)HD * Mp;
+  const uint8_t* blk = kv + ((int64_t)b * H + h) * 6 * n;
+  const int RK = min(HD, (BC_STAGE_BYTES / (Mp * 3)) & ~1);
+  const int nkc = (HD + RK - 1) / RK;
+  constexpr int VR = BC_STAGE_BYTES / (HD * 3);
+  const int nvc = (Mp + VR - 1) / VR;
+  griddep_launch();
+  if (tid == 0) {
+    for (int s = 0; s < BC_NST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < nkc + nvc; ++c) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint8_t *src_hi, *src_lo;
+        uint32_t bytes_lo;
+        if (c < nkc) {
+          const int r0 = c * RK, rows = min(RK, HD - r0);
+          src_hi = blk + (int64_t)r0 * Mp * 2;
+          src_lo = blk + 2 * n + (int64_t)r0 * Mp;
+          bytes_lo = (uint32_t)rows * Mp;
+        } else {
+          const int m0 = (c - nkc) * VR, rows = min(VR, Mp - m0);
+          src_hi = blk + 3 * n + (int64_t)m0 * HD * 2;
+          src_lo = blk + 5 * n + (int64_t)m0 * HD;
+          bytes_lo = (uint32_t)rows * HD;
+        }
+        uint8_t* dst = ring + s * BC_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], 3 * bytes_lo);
+        bulk_load_1d(dst, src_hi, 2 * bytes_lo, &full_bar[s]);
+        bulk_load_1d(dst + 2 * bytes_lo, src_lo, bytes_lo, &full_bar[s]);
+        if (++s == BC_NST) { s = 0; ph ^= 1; }
+      }
+    }
+    griddep_wait();
+    return;
+  }
+  griddep_wait();
+  for (int i = tid; i < nq * HD; i += 256) sq[i] = q[((int64_t)b * nq + i / HD) * D + h * HD + (i % HD)];
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  int s = 0;
+  uint32_t ph = 0;
+  const int npair = Mp >> 1;
+  float acc[BM_MAXNB][BC_MAXK];  // acc[k][2i], acc[k][2i+1] = keys 2*(tid + 256 i), +1 of beam k
+#pragma unroll
+  for (int k = 0; k < BM_MAXNB; ++k)
+#pragma unroll
+    for (int i = 0; i < BC_MAXK; ++i) acc[k][i] = 0.f;
+  for (int c = 0; c < nkc; ++c) {
+    mbar_wait(&full_bar[s], ph);
+    const uint8_t* buf = ring + s * BC_STAGE_BYTES;
+    const int r0 = c * RK, rows = min(RK, HD - r0);
+    const uint8_t* lo_base = buf + (size_t)rows * Mp * 2;
+    for (int rr = 0; rr < rows; ++rr) {
+      const uint32_t* hrow = reinterpret_cast<const uint32_t*>(buf + (size_t)rr * Mp * 2);
+      const uint16_t* lrow = reinterpret_cast<const uint16_t*>(lo_base + (size_t)rr * Mp);
+      float kvv[BC_MAXK];
+#pragma unroll
+      for (int i = 0; i < BC_MAXK / 2; ++i) {
+        const int pi = tid + 256 * i;
+        uint32_t h2 = 0u, l2 = 0u;
+        if (pi < npair) { h2 = hrow[pi]; l2 = lrow[pi]; }
+        kvv[2 * i] = __uint_as_float(__byte_perm(h2, l2, 0x1046));
+        kvv[2 * i + 1] = __uint_as_float(__byte_perm(h2, l2, 0x3256));
+      }
+#pragma unroll
+      for (int k = 0; k < BM_MAXNB; ++k) {
+        if (k < nq) {
+          const float qd = sq[k * HD + r0 + rr];
+#pragma unroll
+          for (int i = 0; i < BC_MAXK; ++i) acc[k][i] += qd * kvv[i];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (++s == BC_NST) { s = 0; ph ^= 1; }
+  }
+  float inv[BM_MAXNB];
+#pragma unroll
+  for (int k = 0; k < BM_MAXNB; ++k) {
+    inv[k] = 0.f;
+    if (k < nq) {  // nq is uniform across the block: the named barriers below are reached by all 256 threads
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BC_MAXK; ++i) {
+        const int m = 2 * (tid + 256 * (i >> 1)) + (i & 1);
+        if (m < Mp) {
+          acc[k][i] += (mask[(int64_t)b * Mp + m] ? 0.f : -3.4028234663852886e38f);
+          mx = fmaxf(mx, acc[k][i]);
+        }
+      }
+      mx = warp_max(mx);
+      if (lane == 0) s_b[warp] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = s_b[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_b[w]);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < BC_MAXK; ++i) {
+        const int m = 2 * (tid + 256 * (i >> 1)) + (i & 1);
+        if (m < Mp) {
+          const float p = expf(acc[k][i] - mx);
+          sc[(int64_t)k * Mp + m] = p;
+          sum += p;
+        }
+      }
+      sum = warp_sum(sum);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (lane == 0) s_b[warp] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += s_b[w];
+      inv[k] = 1.f / sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  const int r = tid >> 4, cc = tid & 15;
+  float4 a4[BM_MAXNB];
+#pragma unroll
+  for (int k = 0; k < BM_MAXNB; ++k) a4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < nvc; ++c) {
+    mbar_wait(&full_bar[s], ph);
+    const uint8_t* buf = ring + s * BC_STAGE_BYTES;
+    const int m0 = c * VR, rows = min(VR, Mp - m0);
+    const uint8_t* lo_base = buf + (size_t)rows * HD * 2;
+#pragma unroll
+    for (int j = 0; j < (VR + 15) / 16; ++j) {
+      const int jj = r + 16 * j;
+      if (jj < rows) {
+        const uint2 h4 = *reinterpret_cast<const uint2*>(buf + ((size_t)jj * HD + 4 * cc) * 2);
+        const uint32_t l4 = *reinterpret_cast<const uint32_t*>(lo_base + (size_t)jj * HD + 4 * cc);
+        float4 vv;
+        vv.x = __uint_as_float((h4.x << 16) | ((l4 & 0xffu) << 8));
+        vv.y = __uint_as_float((h4.x & 0xffff0000u) | (l4 & 0xff00u));
+        vv.z = __uint_as_float((h4.y << 16) | ((l4 >> 8) & 0xff00u));
+        vv.w = __uint_as_float((h4.y & 0xffff0000u) | ((l4 >> 16) & 0xff00u));
+#pragma unroll
+        for (int k = 0; k < BM_MAXNB; ++k) {
+          if (k < nq) {
+            const float p = sc[(int64_t)k * Mp + m0 + jj];
+            a4[k].x += p * vv.x; a4[k].y += p * vv.y; a4[k].z += p * vv.z; a4[k].w += p * vv.w;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (++s == BC_NST) { s = 0; ph ^= 1; }
+  }
+#pragma unroll
+  for (int k = 0; k < BM_MAXNB; ++k) {
+    if (k < nq) {
+      reinterpret_cast<float4*>(sred)[r * 16 + cc] = a4[k];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < HD) {
+        float o = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) o += sred[rr * HD + tid];
+        ctx[((int64_t)b * nq + k) * D + h * HD + tid] = o * inv[k];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+}
+
+void launch_beam_cross_attn24(cudaStream_t st, const float* q, int B, int nq, int H, int D, const uint8_t* kv, int Mp,
+                              const int* mask, float* ctx) {
+  MG_REQUIRE(D == H * 64, "decoder head_dim must be 64");
+  MG_REQUIRE(nq >= 1 && nq <= BM_MAXNB, "1 <= num_beams <= 8");
+  MG_REQUIRE(Mp % 8 == 0 && Mp <= 256 * BC_MAXK, "cross-attention memory length must be a multiple of 8, <= 2048");
+  const size_t smem = (size_t)BC_NST * BC_STAGE_BYTES + ((size_t)nq * Mp + (size_t)nq * 64 + 16 * 64) * 4 +
+                      2 * BC_NST * 8 + 64;
+  static bool attr = false;
+  if (!attr) {
+    MG_CHECK_CUDA(cudaFuncSetAttribute(beam_cross_attn24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  MG_REQUIRE(smem <= 200 * 1024, "num_beams * memory length too large for the beam cross-attention kernel");
+  dim3 grid(H, B);
+  launch_pdl(beam_cross_attn24_kernel, grid, dim3(288), smem, st, q, kv, mask, Mp, H, D, nq, ctx);
+}
+
 // =====================================================================================================
 // Beam state (per image b, beam k):  run_seq / fin_seq [B][nb][L] i64, run_score / fin_score [B][nb] f32,
 // fin_flag [B][nb] (is_sent_finished), fin_len [B][nb] (generated tokens of the finished hypothesis),
@@ -596,6 +805,9 @@ __global__ void __launch_bounds__(1024) beam_select_kernel(BeamState s, const fl
       reinterpret_cast<float4*>(x_next + (int64_t)(b * nb + k) * D)[c] =
           reinterpret_cast<const float4*>(emb + (int64_t)n_tok[k] * D)[c];
     }
+    if (s.step_tok && tid == 0) s.step_tok[b] = n_tok[0];  // provisional token of the best running beam
+  } else if (s.step_tok && tid == 0) {
+    s.step_tok[b] = -1;
   }
   __syncthreads();
   if (tid == 0) {
@@ -615,6 +827,7 @@ __global__ void __launch_bounds__(1024) beam_select_kernel(BeamState s, const fl
       s.ctrl[4] = 0;
       s.ctrl[5] = 0;
       s.ctrl[0] = step + 1;
+      if (s.step_tok) s.step_tok[gridDim.x] = s.ctrl[2];  // this rank's "done" flag travels with the step's tokens
     }
   }
 }
@@ -635,6 +848,29 @@ __global__ void beam_finalize_kernel(BeamState s, int pad, int64_t* __restrict__
 }
 void launch_beam_finalize(cudaStream_t st, const BeamState& s, int pad, int64_t* out_ids, int* out_len) {
   beam_finalize_kernel<<<s.B, 256, 0, st>>>(s, pad, out_ids, out_len);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
+// multi-GPU beam search, after the per-step all-gather: gathered[r] = {token of the best running beam of each of
+// rank r's B images (-1 once that rank's search is frozen), rank r's done flag}.  Fills the provisional column of the
+// global id matrix (the final sequences replace it after the last step) and counts the ranks still searching.
+__global__ void beam_scatter_step_kernel(const int* __restrict__ gathered, int world, int B, int col, int ld,
+                                         int64_t* __restrict__ all_ids, int* __restrict__ n_not_done) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < world * B) {
+    const int r = i / B, b = i - r * B;
+    const int tok = gathered[r * (B + 1) + b];
+    if (tok >= 0 && col < ld) all_ids[(int64_t)i * ld + col] = tok;
+  }
+  if (i == 0) {
+    int n = 0;
+    for (int r = 0; r < world; ++r) n += gathered[r * (B + 1) + B] == 0;
+    *n_not_done = n;
+  }
+}
+void launch_beam_scatter_step(cudaStream_t st, const int* gathered, int world, int B, int col, int ld, int64_t* all_ids,
+                              int* n_not_done) {
+  beam_scatter_step_kernel<<<(world * B + 127) / 128, 128, 0, st>>>(gathered, world, B, col, ld, all_ids, n_not_done);
   MG_CHECK_CUDA(cudaGetLastError());
 }
 

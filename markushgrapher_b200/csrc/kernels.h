@@ -76,6 +76,7 @@ struct BeamState {
   int* anc1;
   int* ctrl;
   int64_t* tmp_seq;  // [B][nb][L] scratch for the slot permutations
+  int* step_tok = nullptr;  // multi-GPU: [B + 1] token of the best running beam per image (-1 once frozen) + this rank's done flag
   int B, nb, L, anc_ld;
 };
 void launch_beam_self_attn(cudaStream_t st, const float* qkv, int R, int H, int D, float* kt, int64_t kt_ld,
@@ -84,6 +85,12 @@ void launch_beam_self_attn(cudaStream_t st, const float* qkv, int R, int H, int 
                            const int* lut, float* ctx);
 void launch_beam_cross_attn(cudaStream_t st, const float* q, int B, int nq, int H, int D, const float* kt,
                             const float* v, int Mp, const int* mask, float* ctx);
+void launch_beam_cross_attn24(cudaStream_t st, const float* q, int B, int nq, int H, int D, const uint8_t* kv, int Mp,
+                              const int* mask, float* ctx);
+// multi-GPU beam search: gathered [world][B + 1] (tokens + done flag per rank) -> provisional column `col` of all_ids,
+// *n_not_done = ranks whose stop condition has not been reached
+void launch_beam_scatter_step(cudaStream_t st, const int* gathered, int world, int B, int col, int ld, int64_t* all_ids,
+                              int* n_not_done);
 void launch_beam_init(cudaStream_t st, const BeamState& s, const float* emb, int D, int start, int pad, float* x);
 void launch_beam_select(cudaStream_t st, const BeamState& s, const float* logits, int V, int64_t ld, const float* emb,
                         int D, int eos, int max_length, float* x_next);

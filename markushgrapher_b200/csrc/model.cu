@@ -1245,8 +1245,13 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
   a.reset();
   const int Tp = (int)rup(max_length, 4);
   const int64_t Vld = rup(V, 4);
+  // cross K/V as kv24 blocks (3 bytes / element, decode.cu) streamed once per IMAGE for all its beams, unless MG_KV24=0
+  const bool env_kv24 = !(getenv("MG_KV24") && getenv("MG_KV24")[0] == '0');
+  const bool kv24 = env_kv24 && Mp % 8 == 0 && Mp <= 2048;
   std::vector<float*> ckt(NL), cv(NL);
-  project_cross_kv(st, B, ckt, cv);
+  std::vector<uint8_t*> ckv(NL, nullptr);
+  project_cross_kv(st, B, ckt, cv, kv24 ? &ckv : nullptr);
+  const bool dist = comm != nullptr && dist_all_ids != nullptr;
   std::vector<float*> skt(NL), sv(NL);
   for (int l = 0; l < NL; ++l) {
     skt[l] = a.get<float>((int64_t)R * d * Tp);
@@ -1271,6 +1276,15 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
   bs.anc0 = a.get<int>((int64_t)R * Tp);
   bs.anc1 = a.get<int>((int64_t)R * Tp);
   bs.ctrl = a.get<int>(8);
+  int* gathered = nullptr;
+  int* gctr = a.get<int>(4);  // [0] = ranks whose search is not done (multi-GPU)
+  if (dist) {
+    bs.step_tok = a.get<int>(B + 1);
+    gathered = a.get<int>((int64_t)world * (B + 1));
+    MG_CHECK_CUDA(cudaMemsetAsync(bs.step_tok, 0, sizeof(int) * (size_t)(B + 1), st));
+    MG_CHECK_CUDA(cudaMemcpyAsync(gctr, &world, sizeof(int), cudaMemcpyHostToDevice, st));
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));  // `world` is read by the copy
+  }
   // fill value of unfinished tail positions: stock transformers computes `pad_token_id or eos_token_id[0]`
   // (generation/utils.py:3165), i.e. EOS when the pad id is 0 as it is for UDOP/T5 -- mirrored for id parity
   const int fill = c.pad_token_id != 0 ? c.pad_token_id : c.eos_token_id;
@@ -1297,7 +1311,10 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
                             bs.ctrl + 1, bs.anc0, bs.anc1, Tp, dec_bias, lut_dec, ctx);
       lin(0, ctx, d, L.o, x, d, nullptr, 1.f, nullptr, 0, false);
       lin(1, x, d, L.cq, q, d, L.ln2, 1.f, qkv, (int64_t)R * 3 * d, false);
-      launch_beam_cross_attn(st, q, B, nb, H, d, ckt[l], cv[l], Mp, mem_mask, ctx);
+      if (kv24)
+        launch_beam_cross_attn24(st, q, B, nb, H, d, ckv[l], Mp, mem_mask, ctx);
+      else
+        launch_beam_cross_attn(st, q, B, nb, H, d, ckt[l], cv[l], Mp, mem_mask, ctx);
       lin(0, ctx, d, L.co, x, d, nullptr, 1.f, nullptr, 0, false);
       lin(1, x, d, L.wi, hbuf, c.d_ff, L.ln3, 1.f, q, (int64_t)R * d, false);
       lin(2, hbuf, c.d_ff, L.wo, x, d, nullptr, 1.f, nullptr, 0, false);
@@ -1307,9 +1324,19 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
     launch_beam_select(st, bs, logits, V, Vld, shared, d, c.eos_token_id, max_length, x);
     launches += 1;
   };
+  // multi-GPU: one all-gather per step of {token of every image's best running beam, this rank's done flag}; every rank
+  // keeps stepping (frozen once its own search is done) until ALL ranks are done, so all stop on the same step
+  auto exchange = [&](int col) {
+    MG_CHECK_NCCL(nccl_api().AllGather(bs.step_tok, gathered, (size_t)(B + 1), ncclInt32, comm, st));
+    launch_beam_scatter_step(st, gathered, world, B, col, max_length, dist_all_ids, gctr);
+    launches += 2;
+  };
+  if (dist) MG_CHECK_CUDA(cudaMemsetAsync(dist_all_ids, 0, sizeof(int64_t) * (size_t)world * B * max_length, st));
   const int total_steps = max_length - 1;
+  MG_CHECK_CUDA(cudaEventRecord(ev_loop[0], st));
   one_step();
   int done_steps = 1;
+  if (dist) exchange(1);
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   if (total_steps > 1) {
@@ -1326,22 +1353,34 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
     MG_CHECK_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
     const int64_t step_launches = launches - before;
     launches = before;
-    pinned_flag[0] = 0;  // "done" flag of the device-side stop rule
+    pinned_flag[0] = dist ? world : 0;  // device-side stop rule: "done" flag, or (multi-GPU) ranks not yet done
     bool stop = false;
     while (done_steps < total_steps && !stop) {
       const int n = std::min(16, total_steps - done_steps);
-      for (int i = 0; i < n; ++i) MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+      for (int i = 0; i < n; ++i) {
+        MG_CHECK_CUDA(cudaGraphLaunch(gexec, st));
+        if (dist) exchange(done_steps + i + 1);
+      }
       launches += step_launches * n;
       done_steps += n;
       MG_CHECK_CUDA(cudaEventSynchronize(ev[3]));
-      if (pinned_flag[0] != 0) stop = true;
-      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, bs.ctrl + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (dist ? pinned_flag[0] == 0 : pinned_flag[0] != 0) stop = true;
+      MG_CHECK_CUDA(cudaMemcpyAsync(pinned_flag, dist ? gctr : bs.ctrl + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
       MG_CHECK_CUDA(cudaEventRecord(ev[3], st));
     }
   }
   launch_beam_finalize(st, bs, fill, out_ids, out_len);
   ++launches;
+  MG_CHECK_CUDA(cudaEventRecord(ev_loop[1], st));
+  if (dist) {  // the final sequences of every rank's images, in global image order
+    MG_CHECK_NCCL(nccl_api().AllGather(out_ids, dist_all_ids, (size_t)B * max_length, ncclInt64, comm, st));
+    ++launches;
+  }
   MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  MG_CHECK_CUDA(cudaEventElapsedTime(&last_loop_ms, ev_loop[0], ev_loop[1]));
+  last_loop_steps = done_steps;
+  last_fused = 0;
+  last_step_p50_ms = last_step_p99_ms = 0.f;
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   if (steps_run) *steps_run = done_steps;
@@ -1480,31 +1519,33 @@ int mg_comm_init(mg_model* m, int world, int rank, const void* id_128_bytes) {
 }
 
 int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64_t* input_ids, const float* bbox,
-                     const float* pixel_values, const int64_t* attn_mask, int max_length, int64_t* all_ids,
+                     const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length, int64_t* all_ids,
                      int32_t* steps_run) {
   MG_API_BEGIN
   MG_REQUIRE(m && m->comm, "mg_comm_init has not been called");
   MG_REQUIRE(all_ids, "null argument");
+  MG_REQUIRE(num_beams >= 1 && num_beams <= 8, "1 <= num_beams <= 8");
   {  // every rank must bring the same shard size and length: unequal counts would hang or corrupt the all-gather
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    if (!m->dist_chk) m->dist_chk = m->own<int>(2 + 2 * 64);
+    if (!m->dist_chk) m->dist_chk = m->own<int>(4 + 4 * 64);
     MG_REQUIRE(m->world <= 64, "at most 64 ranks");
-    const int mine[2] = {B_local, max_length};
+    const int mine[4] = {B_local, max_length, num_beams, 0};
     MG_CHECK_CUDA(cudaMemcpyAsync(m->dist_chk, mine, sizeof(mine), cudaMemcpyHostToDevice, cs));
-    MG_CHECK_NCCL(nccl_api().AllGather(m->dist_chk, m->dist_chk + 2, 2, ncclInt32, m->comm, cs));
-    std::vector<int> all((size_t)2 * m->world);
-    MG_CHECK_CUDA(cudaMemcpyAsync(all.data(), m->dist_chk + 2, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, cs));
+    MG_CHECK_NCCL(nccl_api().AllGather(m->dist_chk, m->dist_chk + 4, 4, ncclInt32, m->comm, cs));
+    std::vector<int> all((size_t)4 * m->world);
+    MG_CHECK_CUDA(cudaMemcpyAsync(all.data(), m->dist_chk + 4, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, cs));
     MG_CHECK_CUDA(cudaStreamSynchronize(cs));
     for (int r = 0; r < m->world; ++r)
-      MG_REQUIRE(all[2 * r] == B_local && all[2 * r + 1] == max_length,
-                 "mg_generate_dist: rank " + std::to_string(r) + " brought B_local=" + std::to_string(all[2 * r]) +
-                     " max_length=" + std::to_string(all[2 * r + 1]) + ", this rank B_local=" + std::to_string(B_local) +
-                     " max_length=" + std::to_string(max_length) + " (pad the shards to one size)");
+      MG_REQUIRE(all[4 * r] == B_local && all[4 * r + 1] == max_length && all[4 * r + 2] == num_beams,
+                 "mg_generate_dist: rank " + std::to_string(r) + " brought B_local=" + std::to_string(all[4 * r]) +
+                     " max_length=" + std::to_string(all[4 * r + 1]) + " num_beams=" + std::to_string(all[4 * r + 2]) +
+                     ", this rank B_local=" + std::to_string(B_local) + " max_length=" + std::to_string(max_length) +
+                     " num_beams=" + std::to_string(num_beams) + " (pad the shards to one size)");
   }
   int64_t* local = m->persist_ids((int64_t)B_local * max_length);
   m->dist_all_ids = all_ids;
-  int rc = mg_generate(m, stream, B_local, Lt, input_ids, bbox, pixel_values, attn_mask, 1, max_length, local, nullptr,
-                       nullptr, steps_run);
+  int rc = mg_generate(m, stream, B_local, Lt, input_ids, bbox, pixel_values, attn_mask, num_beams, max_length, local,
+                       nullptr, nullptr, steps_run);
   m->dist_all_ids = nullptr;
   if (rc != 0) return rc;
   MG_API_END

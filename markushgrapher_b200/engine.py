@@ -209,17 +209,17 @@ class MGEngine:
             _lib.check(L.mg_comm_init(self._h, world, rank, box[0]), "mg_comm_init")
         self.world, self.rank = world, rank
 
-    def generate_dist(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512):
+    def generate_dist(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512, num_beams=1):
         """this rank's shard in, ids of the WHOLE batch (world*B_local, max_length) out, on every rank"""
         ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
         out = torch.empty((self.world * B, max_length), device=self.device, dtype=torch.int64)
         steps = ctypes.c_int32(0)
         L = _lib.lib()
         L.mg_generate_dist.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] +
-                                       [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p])
+                                       [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p])
         with torch.cuda.device(self.device):
             rc = L.mg_generate_dist(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px),
-                                    _lib.ptr(am), int(max_length), _lib.ptr(out), ctypes.addressof(steps))
+                                    _lib.ptr(am), int(num_beams), int(max_length), _lib.ptr(out), ctypes.addressof(steps))
         _lib.check(rc, "mg_generate_dist")
         self.last_steps = steps.value
         return out

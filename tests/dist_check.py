@@ -1,5 +1,7 @@
 """torchrun --nproc-per-node N tests/dist_check.py : every rank decodes its shard, the per-step NCCL all-gather
-must give every rank the ids of the whole batch == the oracle's ids for the whole batch."""
+must give every rank the ids of the whole batch == the oracle's ids for the whole batch -- greedy, beam search
+(beams of an image stay on its GPU; stock GenerationMixin._beam_search on the oracle is the reference), and the
+shard-shape handshake (unequal shards must fail on every rank with a message, not hang)."""
 import os
 import sys
 
@@ -25,6 +27,29 @@ ids = eng.generate_dist(**{k: v[lo:hi] for k, v in inp.items()}, max_length=18).
 ref = oracle.generate_greedy(**inp, max_length=18)
 ok = torch.equal(ids[:, : ref.shape[1]], ref)
 print(f"rank {rank}/{world}: all-gathered ids {tuple(ids.shape)} match oracle for the whole batch: {ok}")
+# beam search, 4 beams: early-EOS made likely so that ranks finish their searches on different steps
+import copy
+o2 = copy.deepcopy(oracle)
+with torch.no_grad():
+    o2.lm_head.weight[1] = o2.lm_head.weight[1] * 0.0 + o2.lm_head.weight[7] * 1.5 + o2.lm_head.weight[11] * 1.5
+eng2 = MGEngine(cfg, o2.export_state(), device=torch.device("cuda", local))
+eng2.comm_init_from_torch()
+inp2 = O.make_inputs(cfg, n, 14, seed=77)
+bids = eng2.generate_dist(**{k: v[lo:hi] for k, v in inp2.items()}, max_length=40, num_beams=4).cpu()
+bref = o2.hf_generate(**inp2, max_length=40, num_beams=4)
+okb = torch.equal(bids[:, : bref.shape[1]], bref) and bool((bids[:, bref.shape[1]:] == 1).all())
+print(f"rank {rank}/{world}: beam-4 ids {tuple(bids.shape)} match stock beam search for the whole batch: {okb}")
+ok = ok and okb
+# unequal shards: every rank gets an error naming the offender
+if world > 1:
+    from markushgrapher_b200._lib import MgError
+    nb = 2 if rank == 0 else 1
+    try:
+        eng.generate_dist(**{k: v[:nb] for k, v in inp.items()}, max_length=18)
+        ok = False
+        print(f"rank {rank}: unequal shards were NOT rejected")
+    except MgError as e:
+        print(f"rank {rank}: unequal shards rejected: {str(e)[:120]}")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

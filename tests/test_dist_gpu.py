@@ -31,4 +31,8 @@ def test_single_rank_nccl_generate_matches_plain_generate():
     dist_ids = eng.generate_dist(**inp, max_length=18)
     assert torch.equal(dist_ids, plain)
     assert torch.equal(dist_ids.cpu()[:, : ref.shape[1]], ref)
+    # beam search through the sharded entry (single rank): same ids as the plain call
+    beam_plain = eng.generate(**inp, max_length=18, num_beams=4, trim=False)
+    beam_dist = eng.generate_dist(**inp, max_length=18, num_beams=4)
+    assert torch.equal(beam_dist, beam_plain)
     eng.close()
