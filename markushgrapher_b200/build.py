@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = ["gemm_tc.cu", "ops.cu", "swin.cu", "decode.cu", "decode_mega.cu", "beam.cu", "model.cu", "api_ops.cu", "pack.cu", "detok.cu"]
+SRC = ["gemm_tc.cu", "ops.cu", "enc_flash.cu", "swin.cu", "decode.cu", "decode_mega.cu", "beam.cu", "model.cu", "api_ops.cu", "pack.cu", "detok.cu"]
 OUT = os.path.join(HERE, "lib", "libmg_b200.so")
 
 

@@ -64,6 +64,18 @@ constexpr int MK_CROSS_VR = 208;  // keys per cross-V chunk (kv24: 192 bytes per
 #define MK_STAMP(ptr, i) do { } while (0)
 #endif
 
+// CTA-local progress flags (producer -> consumers "loads issued" counter, consumers -> producer phase counter) are
+// plain volatile shared words: single writer, monotonic, readers spin.  compute-sanitizer racecheck reports every
+// spin read as a hazard (10^7 of them); the -DMK_RACECHECK build routes the flag accesses through shared-memory
+// atomics, which racecheck treats as synchronising, so that any OTHER hazard becomes visible.
+#ifdef MK_RACECHECK
+#define MK_FLAG_LD(p) atomicAdd(const_cast<int*>(p), 0)
+#define MK_FLAG_ST(p, v) atomicExch(const_cast<int*>(p), (v))
+#else
+#define MK_FLAG_LD(p) (*(p))
+#define MK_FLAG_ST(p, v) (*(p) = (v))
+#endif
+
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 // mbarrier wait shared by every role (one copy in the instruction cache); bounded: a hang becomes a trap
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               // prefetch gate: this phase's K/V stream starts when the CTA's consumers have entered the phase
               const int want = l * MK_NPH + ph;
               const long long t0 = clock64();
-              while (*s_phase < want)
+              while (MK_FLAG_LD(s_phase) < want)
                 if (clock64() - t0 > 4000000000LL) mk_die(2, want, *s_phase);
             }
             n_items = n_attn;
@@ -403,7 +415,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                         : "memory");
                   r.adv();
                   __threadfence_block();
-                  *s_issued = n_put;
+                  MK_FLAG_ST(s_issued, n_put);
                 }
               }
             }
@@ -587,7 +599,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                   {
                     const int seq = r.n + c * ng + gi;
                     uint32_t spins = 0;
-                    while (*s_issued <= seq)
+                    while (MK_FLAG_LD(s_issued) <= seq)
                       if (++spins > (1u << 26)) mk_die(4, (uint32_t)seq, (uint32_t)*s_issued);
                   }
                   mk_wait(bar_full + 8 * st, par);
@@ -652,7 +664,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                   {
                     const int seq = r.n + (self_nkc + c) * ng + gi;
                     uint32_t spins = 0;
-                    while (*s_issued <= seq)
+                    while (MK_FLAG_LD(s_issued) <= seq)
                       if (++spins > (1u << 26)) mk_die(4, (uint32_t)seq, (uint32_t)*s_issued);
                   }
                   mk_wait(bar_full + 8 * st, par);
@@ -1080,7 +1092,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             if (clock64() - t0 > 4000000000LL) mk_die(3, v, bar_target);
           }
           MK_STAMP(ps, 1);
-          *s_phase = phase_i + 1;  // consumers enter the next phase (releases the producer's prefetch gate)
+          MK_FLAG_ST(s_phase, phase_i + 1);  // consumers enter the next phase (releases the producer's prefetch gate)
         }
         ++phase_i;
         cons_sync();

@@ -351,6 +351,12 @@ static void encode_operand(CUtensorMap* map, const bf16* ptr, const GemmOperand&
                         std::to_string(K) + " rows=" + std::to_string(op.rows) + " ld=" + std::to_string(op.ld) + ")");
 }
 
+// TMA descriptor of a K-major bf16 operand [nb][rows][inner] (128-byte swizzle, box = 64 x box_rows) for kernels outside
+// this file (enc_flash.cu); coordinates are (inner, row, batch, 0)
+void make_tmap_bf16(CUtensorMap* map, const bf16* ptr, const GemmOperand& op, int inner, int nb, int box_rows) {
+  encode_operand(map, ptr, op, inner, nb, 1, box_rows);
+}
+
 template <int BN>
 static void launch_bn(cudaStream_t st, const GemmParams& p, dim3 grid) {
   static bool attr_set = false;
@@ -572,6 +578,7 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
           if (lane == 0) s_part[(r0 + j) * 4 + wq] = ss;
         }
       }
+      __syncwarp();  // reconverge after the lane-0 stores: bar.sync is .aligned (compute-sanitizer synccheck)
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (t < R) {
         const float ss = (s_part[t * 4] + s_part[t * 4 + 1]) + (s_part[t * 4 + 2] + s_part[t * 4 + 3]);
@@ -580,6 +587,7 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
     } else {
       if (t < R) s_rs[t] = p.scale;
     }
+    __syncwarp();
     asm volatile("bar.sync 3, 256;" ::: "memory");
   } else {
     // ---------------------------------------------------------------- workers (warps 2..5, 128 threads)
@@ -648,6 +656,7 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
       for (int64_t i = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + t; i < n4; i += nthreads)
         z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    __syncwarp();
     asm volatile("bar.sync 3, 256;" ::: "memory");  // row scales s_rs[] published by the statistic warps
     // ---------------------------------------------------------------- epilogue
     mbar_wait(tmem_full_bar, 0);
@@ -690,6 +699,7 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
       }
     }
     if (p.amax_val) {
+      __syncwarp();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (t < p.B) {
         const int* s_pi = reinterpret_cast<const int*>(s_rs + R * 5);
@@ -747,6 +757,12 @@ void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes 
   ksplit = (p.num_kb + p.kb_per_cta - 1) / p.kb_per_cta;
   static const int max_stages = getenv("MG_SKINNY_STAGES") ? atoi(getenv("MG_SKINNY_STAGES")) : 4;
   p.stages = std::min(max_stages, p.kb_per_cta);  // <= 84 KB: CTAs of consecutive (PDL-overlapped) kernels co-reside
+  {  // the ring must fit the 200 KB this kernel may use: a stage grows with the activation rows (64 KB at 65..128 rows)
+    const int ng = B <= 32 ? 1 : (B <= 64 ? 2 : 4);
+    const int stage = 2 * A_BYTES + 2 * (32 * ng * BK * 2);
+    const int fixed = 1024 + 256 + 32 * ng * 9 * 4 + 64;
+    p.stages = std::max(1, std::min(p.stages, (200 * 1024 - fixed) / stage));
+  }
   p.pro = pro; p.lnw = lnw; p.eps = eps; p.scale = scale;
   p.zero_ptr = zero_ptr; p.zero_n = zero_n; p.store = store ? 1 : 0;
   p.amax_val = amax_val; p.amax_idx = amax_idx;

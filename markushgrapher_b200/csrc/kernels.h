@@ -23,6 +23,15 @@ void launch_enc_softmax(cudaStream_t st, const float* scores, const uchar2* hv, 
 void launch_fill_f32(cudaStream_t st, float* p, int64_t n, float v);
 void launch_build_mem_mask(cudaStream_t st, const int* vtl_mask, int B, int Sp, int S, int n_sw, int Mp, int* out);
 
+// ---- enc_flash.cu: fused encoder self-attention (scores, bucketed bias, online softmax, P.V in one tcgen05 kernel)
+size_t enc_bias_code_bytes(int B, int Sp);
+void launch_enc_bias_code(cudaStream_t st, const double* bbox_ext, const int* mask, int B, int Sp, const int* lut_hv,
+                          int lut_n, int half_buckets, uint16_t* code);
+// qk planes [B*Sp][2D] (q | k), vt planes [B][D][Sp], ctx planes [B*Sp][D]
+void launch_enc_flash_attn(cudaStream_t st, Planes qk, Planes vt, const uint16_t* code, const float* tab1d,
+                           const float* tabh, const float* tabv, const int* lut1d, int lut1d_n, int half_buckets,
+                           int nbuckets, int B, int H, int D, int Sp, Planes ctx);
+
 // ---- swin.cu
 void launch_resize_bilinear(cudaStream_t st, const float* in, int B, int Hi, int Wi, int Ho, int Wo, float* out);
 void launch_window_rowmap(cudaStream_t st, int B, int Hs, int Ws, int ws, int shift, int* map);

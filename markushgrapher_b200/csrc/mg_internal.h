@@ -79,6 +79,10 @@ struct GemmEpilogue {
 void launch_gemm(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int nb1, int nb2,
                  int ksplit, const GemmEpilogue& ep, int block_n);
 
+// TMA descriptor (128-byte swizzle, box 64 x box_rows) of a K-major bf16 operand batched along bs1: coordinates
+// (inner, row, batch, 0); rows past op.rows are zero-filled
+void make_tmap_bf16(CUtensorMap* map, const bf16* ptr, const GemmOperand& op, int inner, int nb, int box_rows);
+
 // fp32 [rows, cols] (row stride ld_in) -> planes [rows, ld_out], zero-filling cols..ld_out
 void launch_split(cudaStream_t st, const float* in, int64_t rows, int64_t cols, int64_t ld_in, Planes out,
                   int64_t ld_out);

@@ -733,15 +733,26 @@ void mg_model::vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_
   launch_combine(st, ids, bbox, amask, shared, pemb, cell_x, cell_y, Bc, Lt, np_side, Sp, d, c.max_2d, c.vocab_size,
                  ocr_pt, vis_src, n_vis, x, bbox_ext, vmask);
   launches += 2;
-  uchar2* hv = a.get<uchar2>(T * Sp);
-  launch_relbucket_hv(st, bbox_ext, Bc, Sp, lut_hv, lut_hv_n, c.rel_buckets / 2, hv);
+  // encoder attention: one fused tcgen05 flash kernel per layer (enc_flash.cu); MG_ENC_ATTN=unfused keeps the round-1
+  // chain (scores GEMM -> softmax kernel -> P.V GEMM through a materialised (B,H,S,S) tensor) for A/B runs
+  static const bool env_unfused = getenv("MG_ENC_ATTN") && std::string(getenv("MG_ENC_ATTN")) == "unfused";
+  const bool flash = !env_unfused && split2 && c.rel_buckets <= 32 && Sp <= 1632;
+  uchar2* hv = nullptr;
+  uint16_t* code = nullptr;
+  if (flash) {
+    code = reinterpret_cast<uint16_t*>(a.alloc(enc_bias_code_bytes(Bc, Sp)));
+    launch_enc_bias_code(st, bbox_ext, vmask, Bc, Sp, lut_hv, lut_hv_n, c.rel_buckets / 2, code);
+  } else {
+    hv = a.get<uchar2>(T * Sp);
+    launch_relbucket_hv(st, bbox_ext, Bc, Sp, lut_hv, lut_hv_n, c.rel_buckets / 2, hv);
+  }
   ++launches;
 
   Planes xn = planes(a, T * d);
   Planes qk = planes(a, T * 2 * d);
   Planes vt = planes(a, T * d);  // [Bc][d][Sp]
-  float* scores = a.get<float>((int64_t)Bc * H * Sp * Sp);
-  Planes P = planes(a, (int64_t)Bc * H * Sp * Sp);
+  float* scores = flash ? nullptr : a.get<float>((int64_t)Bc * H * Sp * Sp);
+  Planes P = flash ? Planes{} : planes(a, (int64_t)Bc * H * Sp * Sp);
   Planes ctx = planes(a, T * d);
   Planes hid = planes(a, T * c.d_ff);
 
@@ -767,38 +778,44 @@ void mg_model::vtl_forward(cudaStream_t st, int B0, int Bc, int Lt, const int64_
       launch_gemm(st, A, Bop, d, Sp, d, 1, Bc, 1, ep, 128);
       ++launches;
     }
-    {  // scores[b][h] = q k^T   (no 1/sqrt(d) scaling in T5)
-      GemmOperand A, Bop;
-      A.hi = qk.hi; A.lo = qk.lo; A.rows = Sp; A.ld = 2 * d;
-      A.use_b1 = true; A.bs1 = 64; A.use_b2 = true; A.bs2 = (int64_t)Sp * 2 * d;
-      Bop = A;
-      Bop.hi = qk.hi + d;
-      Bop.lo = qk.lo ? qk.lo + d : nullptr;
-      GemmEpilogue ep;
-      ep.out_f32 = scores;
-      ep.ld_r = Sp;
-      ep.bs1 = (int64_t)Sp * Sp;
-      ep.bs2 = (int64_t)H * Sp * Sp;
-      launch_gemm(st, A, Bop, Sp, Sp, 64, H, Bc, 1, ep, 128);
+    if (flash) {
+      launch_enc_flash_attn(st, qk, vt, code, tab1d, tabh, tabv, lut_enc1d, lut_enc1d_n, c.rel_buckets / 2, c.rel_buckets,
+                            Bc, H, d, Sp, ctx);
       ++launches;
-    }
-    launch_enc_softmax(st, scores, hv, vmask, tab1d, tabh, tabv, lut_enc1d, lut_enc1d_n, c.rel_buckets / 2,
-                       c.rel_buckets, Bc, H, Sp, P);
-    ++launches;
-    {  // ctx[b][:, h*64:(h+1)*64] = P[b][h] . V[b][h]
-      GemmOperand A, Bop;
-      A.hi = P.hi; A.lo = P.lo; A.rows = Sp; A.ld = Sp;
-      A.use_b1 = true; A.bs1 = (int64_t)Sp * Sp; A.use_b2 = true; A.bs2 = (int64_t)H * Sp * Sp;
-      Bop.hi = vt.hi; Bop.lo = vt.lo; Bop.rows = 64; Bop.ld = Sp;
-      Bop.use_b1 = true; Bop.bs1 = (int64_t)64 * Sp; Bop.use_b2 = true; Bop.bs2 = (int64_t)d * Sp;
-      GemmEpilogue ep;
-      ep.out_hi = ctx.hi;
-      ep.out_lo = ctx.lo;
-      ep.ld_r = d;
-      ep.bs1 = 64;
-      ep.bs2 = (int64_t)Sp * d;
-      launch_gemm(st, A, Bop, Sp, 64, Sp, H, Bc, 1, ep, 64);
+    } else {
+      {  // scores[b][h] = q k^T   (no 1/sqrt(d) scaling in T5)
+        GemmOperand A, Bop;
+        A.hi = qk.hi; A.lo = qk.lo; A.rows = Sp; A.ld = 2 * d;
+        A.use_b1 = true; A.bs1 = 64; A.use_b2 = true; A.bs2 = (int64_t)Sp * 2 * d;
+        Bop = A;
+        Bop.hi = qk.hi + d;
+        Bop.lo = qk.lo ? qk.lo + d : nullptr;
+        GemmEpilogue ep;
+        ep.out_f32 = scores;
+        ep.ld_r = Sp;
+        ep.bs1 = (int64_t)Sp * Sp;
+        ep.bs2 = (int64_t)H * Sp * Sp;
+        launch_gemm(st, A, Bop, Sp, Sp, 64, H, Bc, 1, ep, 128);
+        ++launches;
+      }
+      launch_enc_softmax(st, scores, hv, vmask, tab1d, tabh, tabv, lut_enc1d, lut_enc1d_n, c.rel_buckets / 2,
+                         c.rel_buckets, Bc, H, Sp, P);
       ++launches;
+      {  // ctx[b][:, h*64:(h+1)*64] = P[b][h] . V[b][h]
+        GemmOperand A, Bop;
+        A.hi = P.hi; A.lo = P.lo; A.rows = Sp; A.ld = Sp;
+        A.use_b1 = true; A.bs1 = (int64_t)Sp * Sp; A.use_b2 = true; A.bs2 = (int64_t)H * Sp * Sp;
+        Bop.hi = vt.hi; Bop.lo = vt.lo; Bop.rows = 64; Bop.ld = Sp;
+        Bop.use_b1 = true; Bop.bs1 = (int64_t)64 * Sp; Bop.use_b2 = true; Bop.bs2 = (int64_t)d * Sp;
+        GemmEpilogue ep;
+        ep.out_hi = ctx.hi;
+        ep.out_lo = ctx.lo;
+        ep.ld_r = d;
+        ep.bs1 = 64;
+        ep.bs2 = (int64_t)Sp * d;
+        launch_gemm(st, A, Bop, Sp, 64, Sp, H, Bc, 1, ep, 64);
+        ++launches;
+      }
     }
     {
       GemmEpilogue ep;
@@ -1387,7 +1404,11 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
 }
 
 // ================================================================================================= C ABI
-#define MG_API_BEGIN try {
+// (a failed launch of an EARLIER call leaves a non-sticky error behind that the next cudaGetLastError() would report
+// against an innocent kernel: every entry point starts from a clean slate)
+#define MG_API_BEGIN \
+  try {              \
+    cudaGetLastError();
 #define MG_API_END                                        \
   return 0;                                               \
   }                                                       \

@@ -67,7 +67,8 @@ def test_bench_workload_full_511_steps_rows_vs_oracle(full_pair):
     ids2, lg2 = eng.generate(**dev, max_length=512, return_logits=True, trim=False)
     assert torch.equal(ids, ids2)
     n = 4
-    noise = (lg[:n] - lg2[:n]).abs().max().item()   # run-to-run: order of the split-K red.global.add
+    dnoise = (lg[:n] - lg2[:n]).abs().cpu()          # run-to-run: order of the split-K red.global.add
+    noise = dnoise.max().item()
     lg2 = None
     four = {k: v[:n] for k, v in inp.items()}
     ids_ref, lg_ref = oracle.generate_greedy(**four, max_length=512, return_logits=True)
@@ -75,23 +76,29 @@ def test_bench_workload_full_511_steps_rows_vs_oracle(full_pair):
     got = ids[:n].cpu()
     steps = T - 1
     err = (lg[:n, :steps].cpu() - lg_ref).abs()
-    top2 = lg_ref.topk(2, dim=-1).values
-    margin = top2[..., 0] - top2[..., 1]                       # (n, steps)
-    live = torch.ones_like(margin, dtype=torch.bool)           # decisions that count: rows not yet finished
+    top2v, top2i = lg_ref.topk(2, dim=-1)
+    margin = top2v[..., 0] - top2v[..., 1]                       # (n, steps)
+    live = torch.ones_like(margin, dtype=torch.bool)             # decisions that count: rows not yet finished
     for r in range(n):
         pos = (ids_ref[r] == 1).nonzero()
         if len(pos):
             live[r, pos[0, 0]:] = False
-    worst = (margin / err.amax(dim=-1).clamp_min(1e-30))[live].min().item()
+    # what could flip a decision is the error / noise ON its two leading logits
+    err2 = err.gather(-1, top2i).sum(-1)
+    noise2 = dnoise[:, :steps].gather(-1, top2i).sum(-1)
+    worst_err = (margin / err2.clamp_min(1e-30))[live].min().item()
+    worst_noise = (margin / noise2.clamp_min(1e-30))[live].min().item()
     print(f"511-step parity: T_ref {T}, distinct tokens {ids_ref.unique().numel()}, logits rel err "
-          f"{rel_err(lg[:n, :steps], lg_ref):.2e}, max abs logit err {err.max().item():.2e}, run-to-run noise {noise:.2e}, "
-          f"min live top-2 margin {margin[live].min().item():.2e}, min margin/err {worst:.1f}")
+          f"{rel_err(lg[:n, :steps], lg_ref):.2e}, max abs logit err {err.max().item():.2e}, run-to-run noise (max over all "
+          f"logits) {noise:.2e}, min live top-2 margin {margin[live].min().item():.2e}, min margin / (error on the two leading "
+          f"logits) {worst_err:.1f}, min margin / (run-to-run noise on them) {worst_noise:.1f}")
     assert rel_err(lg[:n, :steps], lg_ref) < 1e-3
     assert torch.equal(got[:, :T], ids_ref), "token ids differ from the oracle"
     assert (got[:, T:] == 0).all()
-    # no decision was within reach of the numerical error, nor of the atomics' reordering noise
-    assert worst > 2.0, f"a live decision had top-2 margin only {worst:.2f}x the observed logit error"
-    assert margin[live].min().item() > 10.0 * noise, (margin[live].min().item(), noise)
+    # no decision was within reach of the numerical error, nor of the atomics' reordering noise: the margin of every
+    # live decision exceeds the combined deviation of its two leading logits
+    assert worst_err > 1.0, f"a live decision had a top-2 margin of only {worst_err:.2f}x the observed logit error"
+    assert worst_noise > 2.0, f"a live decision had a top-2 margin of only {worst_noise:.2f}x the run-to-run noise"
 
 
 # ------------------------------------------------------------------------------------------------ (b)
