@@ -357,6 +357,21 @@ void make_tmap_bf16(CUtensorMap* map, const bf16* ptr, const GemmOperand& op, in
   encode_operand(map, ptr, op, inner, nb, 1, box_rows);
 }
 
+// TMA descriptor of an fp32 matrix [rows][cols] (row stride ld elements), 128-byte swizzle, box box_cols x box_rows
+// (box_cols * 4 must be 128 bytes): coordinates (col, row); rows past the matrix are zero-filled
+void make_tmap_f32_2d(CUtensorMap* map, const float* ptr, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
+  MG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0, "fp32 TMA operand must be 16-byte aligned");
+  MG_REQUIRE(box_cols * 4 == 128 && box_rows <= 256, "fp32 TMA box must be 128 bytes wide, <= 256 rows");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-3, "cuTensorMapEncodeTiled (fp32) failed with CUresult " + std::to_string((int)r));
+}
+
 template <int BN>
 static void launch_bn(cudaStream_t st, const GemmParams& p, dim3 grid) {
   static bool attr_set = false;
@@ -557,32 +572,29 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
     const int wq = warp - 6;  // 0..3
     griddep_wait();
     if (p.pro == 1) {
-      // K <= 1024 here (d_model): each thread owns at most two float4 of a row; loads are unconditional
-      // (rows / columns out of range are clamped and weighted by 0) so 16 of them are in flight per batch
+      // K <= 1024 here (d_model).  Warp wq owns rows wq, wq + 4, ...: a lane holds 8 float4 of a row, two rows (16
+      // loads) are in flight per round trip to L2, and a row's sum never leaves its warp -- no block-level combine.
       const int n4row = p.K >> 2;
-      const int ca = min(t, n4row - 1), cb = min(t + 128, n4row - 1);
-      const float wa = t < n4row ? 1.f : 0.f, wb = (t + 128) < n4row ? 1.f : 0.f;
-      for (int r0 = 0; r0 < R; r0 += 8) {
-        float4 qa[8], qb[8];
+#pragma unroll 1
+      for (int r0 = wq; r0 < R; r0 += 8) {
+        float4 qa[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)min(r0 + j, p.B - 1) * p.ldx);
-          qa[j] = xr[ca];
-          qb[j] = xr[cb];
+        for (int u = 0; u < 2; ++u) {
+          const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)min(r0 + 4 * u, p.B - 1) * p.ldx);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) qa[u][i] = xr[min(lane + 32 * i, n4row - 1)];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float ss = wa * (qa[j].x * qa[j].x + qa[j].y * qa[j].y + qa[j].z * qa[j].z + qa[j].w * qa[j].w) +
-                     wb * (qb[j].x * qb[j].x + qb[j].y * qb[j].y + qb[j].z * qb[j].z + qb[j].w * qb[j].w);
+        for (int u = 0; u < 2; ++u) {
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = qa[u][i];
+            ss += (lane + 32 * i < n4row) ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f;
+          }
           ss = warp_sum(ss);
-          if (lane == 0) s_part[(r0 + j) * 4 + wq] = ss;
+          if (lane == 0 && r0 + 4 * u < R) s_rs[r0 + 4 * u] = rsqrtf(ss / (float)p.K + p.eps) * p.scale;
         }
-      }
-      __syncwarp();  // reconverge after the lane-0 stores: bar.sync is .aligned (compute-sanitizer synccheck)
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (t < R) {
-        const float ss = (s_part[t * 4] + s_part[t * 4 + 1]) + (s_part[t * 4 + 2] + s_part[t * 4 + 3]);
-        s_rs[t] = rsqrtf(ss / (float)p.K + p.eps) * p.scale;
       }
     } else {
       if (t < R) s_rs[t] = p.scale;

@@ -83,6 +83,8 @@ void launch_gemm(cudaStream_t st, const GemmOperand& A, const GemmOperand& B, in
 // (inner, row, batch, 0); rows past op.rows are zero-filled
 void make_tmap_bf16(CUtensorMap* map, const bf16* ptr, const GemmOperand& op, int inner, int nb, int box_rows);
 
+void make_tmap_f32_2d(CUtensorMap* map, const float* ptr, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows);
+
 // fp32 [rows, cols] (row stride ld_in) -> planes [rows, ld_out], zero-filling cols..ld_out
 void launch_split(cudaStream_t st, const float* in, int64_t rows, int64_t cols, int64_t ld_in, Planes out,
                   int64_t ld_out);

@@ -5,6 +5,8 @@
 // that MolScribe's encoder wraps (reference requirements.txt:25).
 #include <algorithm>
 
+#include <string>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -222,8 +224,9 @@ void launch_layernorm_any(cudaStream_t st, const float* x, const int* src_rows, 
 // Shifted-window attention (SwinSelfAttention.forward :410-459 + get_attn_mask :556-582), one CTA per
 // (window, head).  qkv: fp32 [rows(window order), 3C] = [q | k | v] with bias already added by the GEMM.
 //   s_ij = (q_i . k_j) / sqrt(hd) + table[(yi-yj+ws-1)*(2ws-1) + (xi-xj+ws-1)][h] + (label_i != label_j ? -100 : 0)
-// K and V of the window sit in shared memory (staged with cp.async.bulk + mbarrier when aligned);
-// each thread owns one query row and runs an online softmax over the ws*ws keys in fp32.
+// Generic fp32 path (any window size; the Swin-B geometry runs window_attn_mma_kernel below): K and V of the window
+// are copied into shared memory with plain vector loads; each thread owns one query row and runs an online softmax
+// over the ws*ws keys with fp32 FMAs.
 template <int HD>
 __global__ void __launch_bounds__(160) window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ table,
                                                           int C, int heads, int ws, int Hs, int Ws, int shift,
@@ -321,9 +324,230 @@ __global__ void __launch_bounds__(160) window_attn_kernel(const float* __restric
   }
 }
 
+
+// =====================================================================================================
+// Shifted-window attention on the tensor cores (the path of every Swin-B block: window 12 -> 144 tokens, head_dim 32).
+// One CTA per (window, head), one warp per 16-row strip of the window (9 warps at 144 tokens):
+//   * the window's q / k / v slices -- 144 rows x 128 bytes each, strided in the fp32 qkv matrix -- are staged into
+//     shared memory by THREE TMA tile loads (cp.async.bulk.tensor.2d, 128-byte swizzle, one mbarrier);
+//   * S = Q K^T and O = P V run as warp-level bf16 MMAs (m16n8k16, fp32 accumulate) on split planes: every fp32
+//     operand is split into hi + lo bf16 while its fragment is built and three products (lo*hi + hi*lo + hi*hi)
+//     restore ~fp32 accuracy, the same numerics policy as the tcgen05 GEMMs.  A 144 x 144 x 32 problem per (window,
+//     head) fills 16-row strips exactly; a 128-row tcgen05 tile would idle 44 % of its rows;
+//   * the whole score row (144 keys) of a strip lives in registers: scale 1/sqrt(32), relative-position bias from the
+//     (2 ws - 1)^2 table, shift mask (-100 across region labels), exact fp32 softmax -- no online rescaling -- and the
+//     probabilities feed the P V MMAs straight from the accumulator fragments.
+// SwinSelfAttention.forward (TF/models/swin/modeling_swin.py:410-459), get_attn_mask (:556-582).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x, y) fp32 -> packed bf16x2 hi and lo planes (x in the low half)
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 f = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// element (row r, column c) of a [rows][32] fp32 tile stored by TMA with the 128-byte swizzle
+__device__ __forceinline__ const float* sw_at(const float* tile, int r, int c) {
+  return tile + r * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));
+}
+
+constexpr int WA_T = 144;      // tokens per window (12 x 12)
+constexpr int WA_NT = WA_T / 8;   // 18 key tiles of 8
+constexpr int WA_WARPS = WA_T / 16;
+
+struct alignas(64) WinAttnParams {
+  CUtensorMap tq;  // fp32 qkv [rows][3C], box 32 x 144
+  const float* table;
+  bf16 *out_hi, *out_lo;
+  int C, heads, ws, Hs, Ws, shift;
+};
+
+__global__ void __launch_bounds__(WA_WARPS * 32) window_attn_mma_kernel(const __grid_constant__ WinAttnParams p) {
+  extern __shared__ uint8_t smw_raw[];
+  uint8_t* const sm = smw_raw + ((1024u - (smem_u32(smw_raw) & 1023u)) & 1023u);
+  float* const sq = reinterpret_cast<float*>(sm);                  // [144][32] swizzled
+  float* const sk = sq + WA_T * 32;
+  float* const sv = sk + WA_T * 32;
+  float* const stab = sv + WA_T * 32;                               // [(2 ws - 1)^2]
+  int* const slab = reinterpret_cast<int*>(stab + 23 * 23);         // [144] region label (shift mask)
+  int* const scol = slab + WA_T;                                    // [144] yj * (2 ws - 1) + xj
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(scol + WA_T);
+  const int ws = p.ws, heads = p.heads, C = p.C;
+  const int h = blockIdx.x % heads;
+  const int64_t win = blockIdx.x / heads;
+  const int nWx = p.Ws / ws, nWy = p.Hs / ws;
+  const int wx = (int)(win % nWx), wy = (int)((win / nWx) % nWy);
+  const int64_t row0 = win * WA_T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, 3 * WA_T * 32 * 4);
+    for (int which = 0; which < 3; ++which)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                       smem_u32(sq + which * WA_T * 32)),
+                   "l"(reinterpret_cast<uint64_t>(&p.tq)), "r"(smem_u32(bar)), "r"(which * C + h * 32), "r"((int)row0)
+                   : "memory");
+  }
+  const int tw = 2 * ws - 1;
+  for (int i = tid; i < tw * tw; i += blockDim.x) stab[i] = p.table[(int64_t)i * heads + h];
+  for (int t = tid; t < WA_T; t += blockDim.x) {
+    int lab = 0;
+    const int ty = t / ws, tx = t % ws;
+    if (p.shift > 0) {
+      const int y = wy * ws + ty, x = wx * ws + tx;  // coordinates in the shifted image
+      const int ry = y < p.Hs - ws ? 0 : (y < p.Hs - p.shift ? 1 : 2);
+      const int rx = x < p.Ws - ws ? 0 : (x < p.Ws - p.shift ? 1 : 2);
+      lab = ry * 3 + rx;
+    }
+    slab[t] = lab;
+    scol[t] = ty * tw + tx;
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int r_lo = warp * 16 + g, r_hi = r_lo + 8;  // this thread's two query rows
+  // ---- Q fragments (A operand): 2 k-steps x {hi, lo}
+  uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const int c = ks * 16 + 2 * t4;
+    const float2 a0 = *reinterpret_cast<const float2*>(sw_at(sq, r_lo, c));
+    const float2 a1 = *reinterpret_cast<const float2*>(sw_at(sq, r_hi, c));
+    const float2 a2 = *reinterpret_cast<const float2*>(sw_at(sq, r_lo, c + 8));
+    const float2 a3 = *reinterpret_cast<const float2*>(sw_at(sq, r_hi, c + 8));
+    split2(a0.x, a0.y, qh[ks][0], ql[ks][0]);
+    split2(a1.x, a1.y, qh[ks][1], ql[ks][1]);
+    split2(a2.x, a2.y, qh[ks][2], ql[ks][2]);
+    split2(a3.x, a3.y, qh[ks][3], ql[ks][3]);
+  }
+  // ---- S = Q K^T: 18 key tiles x 2 k-steps x 3 products
+  float s[WA_NT][4];
+#pragma unroll
+  for (int nt = 0; nt < WA_NT; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    const int j = nt * 8 + g;  // key row of this thread's B fragment
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int c = ks * 16 + 2 * t4;
+      const float2 k0 = *reinterpret_cast<const float2*>(sw_at(sk, j, c));
+      const float2 k1 = *reinterpret_cast<const float2*>(sw_at(sk, j, c + 8));
+      uint32_t bh0, bl0, bh1, bl1;
+      split2(k0.x, k0.y, bh0, bl0);
+      split2(k1.x, k1.y, bh1, bl1);
+      mma_bf16_16816(s[nt], ql[ks], bh0, bh1);
+      mma_bf16_16816(s[nt], qh[ks], bl0, bl1);
+      mma_bf16_16816(s[nt], qh[ks], bh0, bh1);
+    }
+  }
+  // ---- scale, relative-position bias, shift mask, exact softmax over the 144 keys of rows r_lo / r_hi
+  const float div = sqrtf(32.f);
+  const int base_lo = (r_lo / ws + ws - 1) * tw + (r_lo % ws + ws - 1), base_hi = (r_hi / ws + ws - 1) * tw + (r_hi % ws + ws - 1);
+  const int lab_lo = slab[r_lo], lab_hi = slab[r_hi];
+  float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < WA_NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + 2 * t4 + e;
+      const int cj = scol[j], lj = slab[j];
+      float a = s[nt][e] / div + stab[base_lo - cj];
+      float b = s[nt][2 + e] / div + stab[base_hi - cj];
+      if (lj != lab_lo) a += -100.0f;
+      if (lj != lab_hi) b += -100.0f;
+      s[nt][e] = a;
+      s[nt][2 + e] = b;
+      m_lo = fmaxf(m_lo, a);
+      m_hi = fmaxf(m_hi, b);
+    }
+  }
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+  m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+  m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+  float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < WA_NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      s[nt][e] = expf(s[nt][e] - m_lo);
+      s[nt][2 + e] = expf(s[nt][2 + e] - m_hi);
+      sum_lo += s[nt][e];
+      sum_hi += s[nt][2 + e];
+    }
+  }
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+  sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+  sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+  // ---- O = P V: 9 k-steps of 16 keys, 4 output tiles of 8 dims, 3 products; P fragments come from the S accumulators
+  float o[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < WA_T / 16; ++kk) {
+    uint32_t ph[4], pl[4];
+    split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+    split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+    split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+    split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+    const int j0 = kk * 16 + 2 * t4;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int d = nt * 8 + g;
+      uint32_t bh0, bl0, bh1, bl1;
+      split2(*sw_at(sv, j0, d), *sw_at(sv, j0 + 1, d), bh0, bl0);
+      split2(*sw_at(sv, j0 + 8, d), *sw_at(sv, j0 + 9, d), bh1, bl1);
+      mma_bf16_16816(o[nt], pl, bh0, bh1);
+      mma_bf16_16816(o[nt], ph, bl0, bl1);
+      mma_bf16_16816(o[nt], ph, bh0, bh1);
+    }
+  }
+  // ---- normalise and write the context planes
+  const float inv_lo = 1.f / sum_lo, inv_hi = 1.f / sum_hi;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int d = h * 32 + nt * 8 + 2 * t4;
+    uint32_t hh, ll;
+    split2(o[nt][0] * inv_lo, o[nt][1] * inv_lo, hh, ll);
+    *reinterpret_cast<uint32_t*>(p.out_hi + (row0 + r_lo) * C + d) = hh;
+    if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (row0 + r_lo) * C + d) = ll;
+    split2(o[nt][2] * inv_hi, o[nt][3] * inv_hi, hh, ll);
+    *reinterpret_cast<uint32_t*>(p.out_hi + (row0 + r_hi) * C + d) = hh;
+    if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + (row0 + r_hi) * C + d) = ll;
+  }
+}
+
 void launch_window_attn(cudaStream_t st, const float* qkv, const float* table, int64_t n_windows, int C, int heads,
                         int ws, int Hs, int Ws, int shift, Planes out) {
   MG_REQUIRE(C / heads == 32, "Swin head_dim must be 32");
+  MG_REQUIRE(n_windows * heads < (1ll << 31), "too many windows");
+  static const bool env_fma = getenv("MG_SWIN_ATTN") && std::string(getenv("MG_SWIN_ATTN")) == "fma";  // A/B switch
+  if (ws * ws == WA_T && out.hi && !env_fma) {  // window 12: the tensor-core kernel
+    WinAttnParams p;
+    make_tmap_f32_2d(&p.tq, qkv, 3 * C, n_windows * WA_T, 3 * C, 32, WA_T);
+    p.table = table; p.out_hi = out.hi; p.out_lo = out.lo;
+    p.C = C; p.heads = heads; p.ws = ws; p.Hs = Hs; p.Ws = Ws; p.shift = shift;
+    const size_t smem = 1024 + (size_t)(3 * WA_T * 32 + 23 * 23) * 4 + 2 * WA_T * 4 + 64;
+    static bool attr2 = false;
+    if (!attr2) {
+      MG_CHECK_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr2 = true;
+    }
+    window_attn_mma_kernel<<<(unsigned)(n_windows * heads), WA_WARPS * 32, smem, st>>>(p);
+    MG_CHECK_CUDA(cudaGetLastError());
+    return;
+  }
   MG_REQUIRE(ws * ws <= 160, "Swin window too large for the attention kernel");
   const int T = ws * ws;
   const size_t smem = (size_t)(2 * T * 32 + (2 * ws - 1) * (2 * ws - 1)) * sizeof(float) + T * sizeof(int);
