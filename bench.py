@@ -294,7 +294,20 @@ def run_ours(args):
     if world > 1:
         eng.comm_init_from_torch()  # NCCL communicator owned by the library: per-step all-gather of token ids
     B = args.batch
-    host = synth_inputs(cfg.image_size, B, TEXT_LEN, seed=1234 + rank, vocab=cfg.vocab_size)
+    nbeams = args.num_beams
+    text_len = TEXT_LEN
+    cfg_name = "configs[1]"
+    if args.workload == "gen128":      # BASELINE.json configs[3]: 128 images per GPU, greedy <= 512 tok, id all-gather per step
+        B, cfg_name = (args.batch if args.batch != BATCH else 128), "configs[3]"
+    elif args.workload == "beam4":     # BASELINE.json configs[4]: IP5-M shape (1000 images / 8 GPUs), beam 4, <= 768 tok
+        B, cfg_name = (args.batch if args.batch != BATCH else 125), "configs[4]"
+        nbeams = args.num_beams if args.num_beams > 1 else 4
+        args.max_length = args.max_length if args.max_length != MAX_LENGTH else 768
+        text_len = 512
+    if text_len == TEXT_LEN:
+        host = synth_inputs(cfg.image_size, B, TEXT_LEN, seed=1234 + rank, vocab=cfg.vocab_size)
+    else:                              # IP5-M shape: ragged OCR text 32..512 tokens
+        host = synth_inputs_ragged(cfg.image_size, B, text_len, seed=1239 + rank, vocab=cfg.vocab_size)
     host = {k: v.pin_memory() for k, v in host.items()}
     # e2e alternates between two host batches so that the H2D copy of batch i+1 (mg_prefetch_host, copy stream) can
     # overlap the decode of batch i -- both copies stay inside the timed region
@@ -311,16 +324,16 @@ def run_ours(args):
 
     def gen_dev():
         if world > 1:
-            return eng.generate_dist(**devin, max_length=args.max_length)
-        return eng.generate(**devin, max_length=args.max_length, trim=False)
+            return eng.generate_dist(**devin, max_length=args.max_length, num_beams=nbeams)
+        return eng.generate(**devin, max_length=args.max_length, num_beams=nbeams, trim=False)
 
     def gen_host(i=0):
         cur, nxt = (host, host_b) if i % 2 == 0 else (host_b, host)
         if world > 1:  # host shard -> device, sharded generate with per-step id exchange, all ids back to the host
             d = {k: v.to(dev, non_blocking=True) for k, v in cur.items()}
-            return eng.generate_dist(**d, max_length=args.max_length).cpu()
+            return eng.generate_dist(**d, max_length=args.max_length, num_beams=nbeams).cpu()
         eng.prefetch_host(**nxt, max_length=args.max_length)  # returns at once; overlaps this batch's decode
-        return eng.generate_host(**cur, max_length=args.max_length, trim=False)
+        return eng.generate_host(**cur, max_length=args.max_length, num_beams=nbeams, trim=False)
 
     stream = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local)
@@ -360,7 +373,7 @@ def run_ours(args):
         ms_e2e_wall = (time.perf_counter() - t0) * 1000.0
         clocks = sampler.stop()
         # ---- dominant kernel, timed alone with CUDA events on its launch stream
-        prof = eng.profile_cross_attn(reps=3)
+        prof = eng.profile_cross_attn(reps=3) if nbeams == 1 else None
 
     t = torch.tensor([ms_dev, max(ms_e2e_dev, ms_e2e_wall)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -372,14 +385,15 @@ def run_ours(args):
         images = B * world * args.steps
         value = images / (ms_dev / 1000.0)
         e2e = images / (ms_e2e / 1000.0)
-        ach = prof["bytes_per_launch"] / (prof["ms_per_launch"] * 1e-3) / 1e9
+        ach = prof["bytes_per_launch"] / (prof["ms_per_launch"] * 1e-3) / 1e9 if prof else 0.0
         # decode-step HBM model: weights (hi+lo planes = 4 B/param) + B*(cross KV + self KV), fp32
-        d, L, M = cfg.d_model, cfg.num_decoder_layers, cfg.swin_tokens + TEXT_LEN + cfg.n_patches
+        d, L, M = cfg.d_model, cfg.num_decoder_layers, cfg.swin_tokens + text_len + cfg.n_patches
         # weights read by one step: q,k,v,o + cross q,o + wi,wo per layer (cross k,v run once per image, not per step)
         w_bytes = 4 * (L * (6 * d * d + 2 * d * cfg.d_ff) + cfg.vocab_size * d)
         # cross K/V: kv24 = 3 bytes per element (fp32 rounded to 24 significant bits); self K/V (mean cached length
         # = half the decode) and weights: 4 bytes
-        step_bytes = w_bytes + B * (L * 2 * M * d * 3 + L * 2 * (steps_run // 2) * d * 4)
+        # (beam search: the cross K/V of an image are streamed once for all its beams, the self K/V once per beam)
+        step_bytes = w_bytes + B * (L * 2 * M * d * 3 + nbeams * L * 2 * (steps_run // 2) * d * 4)
         step_ms = statistics.mean(loop_ms)  # the step loop alone, CUDA events on the launch stream
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -387,9 +401,10 @@ def run_ours(args):
             "vs_baseline": None, "dtype": ("f32 (GEMM operands as hi+lo bf16 planes on tcgen05 = ~16 significant bits per product, fp32 accumulate / "
                                       "residual / softmax; cross K/V stored as kv24 = 24 stored bits, 16 significant)"),
             "data": "synthetic",
-            "config": {"workload": f"configs[1]: batch-{B} synthetic 512x512 images per GPU, random-init "
-                                   f"MarkushGrapher-2 dims (831M params), greedy <={args.max_length} tok",
-                       "images_per_gpu": B, "text_len": TEXT_LEN, "max_length": args.max_length,
+            "config": {"workload": f"{cfg_name}: batch-{B} synthetic 512x512 images per GPU, random-init "
+                                   f"MarkushGrapher-2 dims (831M params), "
+                                   f"{'greedy' if nbeams == 1 else 'beam=' + str(nbeams)} <={args.max_length} tok",
+                       "images_per_gpu": B, "text_len": text_len, "max_length": args.max_length, "num_beams": nbeams,
                        "decode_steps_run": steps_run,
                        "parallelism": f"image-batch sharding x{world}" + (
                            ", ncclAllGather of token ids per decode step" if world > 1 else ""),
@@ -409,6 +424,8 @@ def run_ours(args):
         full = B == 32 and not args.small
         tr_cross, tr_cross_src = profile_traffic("cross_attn_stream24_kernel", "r*_ncu_cross24.txt")
         tr_step, tr_step_src = profile_traffic("decode_step_kernel", "r*_ncu_decode_step.txt")
+        if prof is None:
+            prof = {"bytes_per_launch": None, "ms_per_launch": None, "launches": 0}
         cross = {"kernel": "cross_attn_stream24_kernel (decoder cross-attention over the kv24 encoder memory), timed "
                            "alone back to back over all layers",
                  "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -434,10 +451,17 @@ def run_ours(args):
                                        "K/V at the mean cached length); the kernel alternates HBM-bound attention "
                                        "phases with latency-bound linears separated by grid barriers",
                                "cross_attention_alone": cross}
+        elif nbeams > 1 or B != 32:
+            a2 = step_bytes / (step_ms * 1e-3) / 1e9
+            out["roofline"] = {"kernel": "one decode step of the per-operation kernel chain (skinny_tc_kernel linears, "
+                                         "self-attention, kv24 streaming cross-attention; CUDA-graph replay)",
+                               "bound": "hbm", "achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak,
+                               "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": step_bytes,
+                               "ms_per_launch": step_ms, "launches_timed": steps_run * args.steps}
         else:
             cross["peak_source"] = peak_src
             out["roofline"] = cross
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "generate":
             threads = os.cpu_count() or 1
             c = cpu_bounded_sample(threads, B, args.max_length)
             out["cpu_baseline"] = {"value": c["images_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
@@ -599,8 +623,11 @@ def main():
     ap.add_argument("--max-length", dest="max_length", type=int, default=MAX_LENGTH)
     ap.add_argument("--small", action="store_true", help="debug: small dims (NOT the benchmark config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="generate", choices=["generate", "enc256"],
-                    help="generate = BASELINE.json configs[1] (the bench line); enc256 = configs[2] (encoder only)")
+    ap.add_argument("--workload", default="generate", choices=["generate", "enc256", "gen128", "beam4"],
+                    help="generate = BASELINE.json configs[1] (the bench line); enc256 = configs[2] (encoder only); "
+                         "gen128 = configs[3] per-GPU shape (128 images, greedy); beam4 = configs[4] (125 images, beam 4, "
+                         "<=768 tok, text <=512)")
+    ap.add_argument("--num-beams", dest="num_beams", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -374,10 +374,10 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attn_mma_kernel(const __
   float* const sq = reinterpret_cast<float*>(sm);                  // [144][32] swizzled
   float* const sk = sq + WA_T * 32;
   float* const sv = sk + WA_T * 32;
-  float* const stab = sv + WA_T * 32;                               // [(2 ws - 1)^2]
-  int* const slab = reinterpret_cast<int*>(stab + 23 * 23);         // [144] region label (shift mask)
-  int* const scol = slab + WA_T;                                    // [144] yj * (2 ws - 1) + xj
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(scol + WA_T);
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(sv + WA_T * 32);  // 8-byte aligned: right behind the tiles
+  float* const stab = reinterpret_cast<float*>(bar + 2);             // [(2 ws - 1)^2]
+  int* const slab = reinterpret_cast<int*>(stab + 23 * 23);          // [144] region label (shift mask)
+  int* const scol = slab + WA_T;                                     // [144] yj * (2 ws - 1) + xj
   const int ws = p.ws, heads = p.heads, C = p.C;
   const int h = blockIdx.x % heads;
   const int64_t win = blockIdx.x / heads;
