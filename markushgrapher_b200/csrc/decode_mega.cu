@@ -149,7 +149,19 @@ struct RingPos {
 // linear in its two inputs, so it is accumulated as Wcq' x (extra rows of phase 0, same activation tile as q/k/v) plus
 // (Wcq' Wo) ctx (extra rows of phase 2, same activation tile as o; the 1024^2 product is precomputed at finalize):
 // the separate "cq" phase of the kernel chain -- a whole latency-bound linear and its grid barrier -- is gone.
+// -DMK_FOLD_FF: the cross-attention output projection is folded into the FF input projection as well,
+//   h = Wi' (x1 + Wco ctx) = Wi' x1 + (Wi' Wco) ctx,   Wi' = Wi diag(ln3),
+// so phases 4 (co) and 5 (wi) become ONE three-segment linear -- rows [0, d): Wco on ctx -> dx; rows [d, d + dff):
+// (Wi' Wco) on ctx -> hidden; rows [d + dff, d + 2 dff): Wi' on the raw residual x1 -> hidden -- and the layer has 6
+// phases: 0 qkv|cq, 1 self, 2 o|cq, 3 cross, 4 co|wi, 5 wo.  x1 must stay intact while phase 4 reads it, so Wco ctx
+// goes to a side buffer dx and the wo phase writes the NEXT residual x3 = (x1 + dx) + rs * Wwo relu(h) into the other
+// of two residual buffers (k-slice 0 of every output tile carries x1 + dx); rs = rsqrt(mean((x1 + dx)^2) + eps) is
+// computed by every CTA's statistic warps during the wo phase and applied in its epilogue.
+#ifdef MK_FOLD_FF
+constexpr int MK_NPH = 6;
+#else
 constexpr int MK_NPH = 7;
+#endif
 constexpr int MK_PH_SELF = 1, MK_PH_CROSS = 3;
 __device__ __forceinline__ int mega_lin_of_phase(int ph) { return ph == 0 ? 0 : (ph == 2 ? 1 : ph - 2); }  // 0,2,4,5,6 -> 0..4
 __device__ __forceinline__ int items_of_cta(int total, int g, int G) { return g < total ? (total - g + G - 1) / G : 0; }
@@ -545,6 +557,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
     for (int l = 0; l <= NL; ++l) {
       const MegaLayer& L = s_layers[min(l, NL - 1)];
       const int nph = l < NL ? MK_NPH : 1;
+#ifdef MK_FOLD_FF
+      float* const xin = (l & 1) ? p.xalt : p.x;   // residual stream read by layer l (the LM head reads X[NL & 1])
+      float* const xout = (l & 1) ? p.x : p.xalt;  // written by its wo phase
+#else
+      float* const xin = p.x;
+#endif
       for (int ph = 0; ph < nph; ++ph) {
         if (l < NL && ph == MK_PH_SELF) {
           // ---------------------------------------------------------------------------------- self-attention
@@ -720,7 +738,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               if (ct < 64) s_q[ct] = __ldcg(p.q + (int64_t)b * D + h * 64 + ct);
               float4 xr = make_float4(0.f, 0.f, 0.f, 0.f);
               const bool new_b = b != rs_b;  // CTA-uniform
-              if (new_b && 4 * ct < D) xr = ldcg4(p.x + (int64_t)b * D + 4 * ct);
+              if (new_b && 4 * ct < D) xr = ldcg4(xin + (int64_t)b * D + 4 * ct);
               int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
 #pragma unroll
               for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
@@ -841,26 +859,42 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           // LM head only: rs * d_model^-0.5 applied in the epilogue (the logits are the final output).
           // (input, prologue, output, which buffer this phase zeroes for a later one):
           int pro = 1, ldx = D, ld_out = D, ld_out2 = D, rs_slot = -1;
-          const float* x = p.x;
-          float* out = p.x;
+          const float* x = xin;
+          float* out = xin;
           float* out2 = p.q;  // rows >= W.n_split of a two-output linear (phases 0 and 2) go to the cross query
           const float* lnw = nullptr;
           float* zero_ptr = nullptr;
           int64_t zero_n = 0;
           const bool store = l == NL;
+          bool wo_fold = false;  // MK_FOLD_FF wo phase: epilogue scales by rs[b] and k-slice 0 adds the residual x1 + dx
           if (store) {  // LM head: final RMSNorm * d_model^-0.5 fused, direct store + per-tile argmax
             lnw = p.final_ln; out = p.logits; ld_out = p.ld_logits;
           } else if (ph == 0) {  // raw x -> qkv | q (ln1 / ln2 are folded into the weight rows); zero: FF hidden buffer
             pro = 0; out = p.qkv; ld_out = 3 * D; zero_ptr = p.hbuf; zero_n = (int64_t)B * p.DFF; rs_slot = 0;
-          } else if (ph == 2) {  // self-attention ctx -> x (+=) | q (+=); zero: qkv (consumed by phase 1)
-            pro = 0; x = p.ctx; zero_ptr = p.qkv; zero_n = (int64_t)B * 3 * D;
-          } else if (ph == 4) {  // cross-attention ctx -> x (+=)
+          } else if (ph == 2) {  // self-attention ctx -> x (+=) | q (+=); zero: qkv (consumed by phase 1) [+ dx behind it]
+            pro = 0; x = p.ctx; zero_ptr = p.qkv;
+#ifdef MK_FOLD_FF
+            zero_n = (int64_t)B * 4 * D;
+#else
+            zero_n = (int64_t)B * 3 * D;
+#endif
+          }
+#ifdef MK_FOLD_FF
+          else if (ph == 4) {  // ctx -> dx | hidden, raw x1 -> hidden (ln3 folded into the columns); zero: the next residual
+            pro = 0; x = p.ctx; out = p.dx; out2 = p.hbuf; ld_out2 = p.DFF; zero_ptr = xout; zero_n = (int64_t)B * D;
+          } else {  // ph == 5: relu(hidden) -> x3 = (x1 + dx) + rs * (Wwo relu(h)); zero: q (consumed by phase 3)
+            pro = 2; x = p.hbuf; ldx = p.DFF; out = xout; wo_fold = true; zero_ptr = p.q; zero_n = (int64_t)B * D;
+          }
+#else
+          else if (ph == 4) {  // cross-attention ctx -> x (+=)
             pro = 0; x = p.ctx;
           } else if (ph == 5) {  // x -> hidden (RMSNorm ln3); zero: q (consumed by phase 3)
             lnw = L.ln[2]; out = p.hbuf; ld_out = p.DFF; zero_ptr = p.q; zero_n = (int64_t)B * D; rs_slot = 2;
           } else {  // ph == 6: rs * relu(hidden) -> x (+=)
             pro = 2; x = p.hbuf; ldx = p.DFF;
           }
+#endif
+          const bool all_rs = store || wo_fold;  // every CTA needs the scale of all rows in its epilogue
           const MegaLin& W = l < NL ? L.lin[mega_lin_of_phase(ph)] : p.lm_head;
           const int items = W.tiles * W.ksplit;
 #ifdef MK_FINE
@@ -869,18 +903,29 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           MK_STAMP(fine, 0);
           if (!is_worker) {
             const int t = ct - 128, wq = cw - 4;
-            if (store) {
-              // LM head: every CTA needs the scale of all 32 rows in its epilogue (warp wq owns rows 8 wq .. 8 wq + 7)
+            if (all_rs) {
+              // LM head / folded wo: every CTA needs the scale of all 32 rows in its epilogue (warp wq owns rows
+              // 8 wq .. 8 wq + 7); the folded wo normalises x1 + dx (the residual after the cross-attention block)
               if (g < items) {
-                const int n4 = W.K >> 2;
+                const int n4 = D >> 2;
+                const float post = store ? p.logit_scale : 1.f;
 #pragma unroll 1
                 for (int rp = 0; rp < 8; rp += 2) {
                   float4 qa[2][8];
 #pragma unroll
                   for (int u = 0; u < 2; ++u) {
-                    const float* xr = x + (int64_t)min(wq * 8 + rp + u, B - 1) * ldx;
+                    const int64_t ro = (int64_t)min(wq * 8 + rp + u, B - 1) * D;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) qa[u][i] = ldcg4(xr + 4 * min(lane + 32 * i, n4 - 1));
+                    for (int i = 0; i < 8; ++i) {
+                      const int c = 4 * min(lane + 32 * i, n4 - 1);
+                      qa[u][i] = ldcg4(xin + ro + c);
+#ifdef MK_FOLD_FF
+                      if (wo_fold) {
+                        const float4 e = ldcg4(p.dx + ro + c);
+                        qa[u][i].x += e.x; qa[u][i].y += e.y; qa[u][i].z += e.z; qa[u][i].w += e.w;
+                      }
+#endif
+                    }
                   }
 #pragma unroll
                   for (int u = 0; u < 2; ++u) {
@@ -891,11 +936,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                       ss += (lane + 32 * i < n4) ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f;
                     }
                     ss = warp_sum(ss);
-                    if (lane == 0) s_rs[wq * 8 + rp + u] = rsqrtf(ss / (float)W.K + p.eps) * p.logit_scale;
+                    if (lane == 0) s_rs[wq * 8 + rp + u] = rsqrtf(ss / (float)D + p.eps) * post;
                   }
                 }
               }
-            } else {
+            }
+            if (!store) {
               if (rs_slot >= 0 && wq == 0 && g < B) {
                 // RMSNorm row scale of image g, consumed one phase later (by other CTAs) through p.rs
                 const int n4 = W.K >> 2;
@@ -924,14 +970,21 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             const int nkb = lin_item_kbs(W, it, tile, kb0);
             if (is_worker) {
               // ---- stage the activation tiles of this item's k-blocks (128 threads)
+#ifdef MK_FOLD_FF
+              // three-segment linear (phase 4): the rows >= n_split2 (Wi') multiply the raw residual, the others ctx
+              const float* xk = ((W.n_split2 && tile * 128 >= W.n_split2) ? xin : x) + kb0 * 64 + c4 * 4;
+#else
               const float* xk = x + kb0 * 64 + c4 * 4;
+#endif
               float4 v[4], gw = make_float4(1.f, 1.f, 1.f, 1.f);
               if (pro == 1) gw = *reinterpret_cast<const float4*>(lnw + kb0 * 64 + c4 * 4);
               float rsr[4] = {1.f, 1.f, 1.f, 1.f};
+#ifndef MK_FOLD_FF
               if (pro == 2) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rsr[i] = __ldcg(p.rs + 2 * MK_R + min(r8 + i * 8, B - 1));
               }
+#endif
 #pragma unroll
               for (int i = 0; i < 4; ++i) v[i] = ldcg4(xk + (int64_t)min(r8 + i * 8, B - 1) * ldx);
 #pragma unroll 1
@@ -977,7 +1030,22 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               r.adv_n(nkb);  // keep this warp's view of the ring in step with the workers / the MMA warp
             }
             MK_STAMP(fine, 2);
-            if (store && first) cons_sync();  // LM head: row scales from the statistic warps
+#ifdef MK_FOLD_FF
+            // folded wo: k-slice 0 of every output tile carries the residual x1 + dx; fetch this thread's 16 values now,
+            // the loads complete under the MMAs (thread = output feature n, columns = images c_lo .. c_lo + 15)
+            const bool add_res = wo_fold && (it % W.ksplit) == 0;
+            float res[16];
+            if (add_res) {
+              const int nn = min(tile * 128 + (warp & 3) * 32 + lane, W.N - 1);
+              const int cl = (cw >> 2) * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int64_t o = (int64_t)min(cl + j, B - 1) * D + nn;
+                res[j] = __ldcg(xin + o) + __ldcg(p.dx + o);
+              }
+            }
+#endif
+            if (all_rs && first) cons_sync();  // LM head / folded wo: row scales from the statistic warps
             first = false;
             // ---- epilogue: TMEM -> registers (thread = output feature, column = image)
             mk_wait(bar_tfull, n_item & 1);
@@ -986,8 +1054,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             const int q = warp & 3;
             int n = tile * 128 + q * 32 + lane, n_lim = W.N, ldo = ld_out;
             float* o_base = out;
-            if (W.n_split) {  // two-output linear, CTA-uniform branch (n_split is a multiple of the tile height)
-              if (tile * 128 >= W.n_split) { n -= W.n_split; n_lim = W.N - W.n_split; o_base = out2; ldo = ld_out2; }
+            if (W.n_split) {  // multi-output linear, CTA-uniform branch (the splits are multiples of the tile height)
+              if (W.n_split2 && tile * 128 >= W.n_split2) { n -= W.n_split2; n_lim = W.N - W.n_split2; o_base = out2; ldo = ld_out2; }
+              else if (tile * 128 >= W.n_split) { n -= W.n_split; n_lim = (W.n_split2 ? W.n_split2 : W.N) - W.n_split; o_base = out2; ldo = ld_out2; }
               else n_lim = W.n_split;
             }
             const bool n_ok = n < n_lim;
@@ -1003,6 +1072,16 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                 uint32_t rr[8];
                 tmem_ld_32x32_x8(taddr + c * 8, rr);
                 tmem_ld_wait();
+#ifdef MK_FOLD_FF
+                if (wo_fold) {  // CTA-uniform
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float v = __uint_as_float(rr[j]) * s_rs[c_lo + c * 8 + j];
+                    if (add_res) v += (c == 0) ? res[j] : res[8 + j];
+                    rr[j] = __float_as_uint(v);
+                  }
+                }
+#endif
                 const int nv = B - (c_lo + c * 8);  // image rows left (warp-uniform)
                 if (n_ok) {
                   if (nv >= 8) {
@@ -1071,7 +1150,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             MK_STAMP(fine, 5);
             ++n_item;
           }
-          if (store && first) cons_sync();
+          if (all_rs && first) cons_sync();
         }
         if (l == NL) break;
         // ------------------------------------------------------------------------------------ grid barrier
@@ -1130,11 +1209,22 @@ __global__ void tile_weights_kernel(const bf16* __restrict__ hi, const bf16* __r
   }
 }
 
-MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst, int n_split) {
+bool mega_fold_ff() {
+#ifdef MK_FOLD_FF
+  return true;
+#else
+  return false;
+#endif
+}
+
+MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst, int n_split,
+                      int n_split2) {
   MG_REQUIRE(n_split % 128 == 0 && n_split < N, "fused decode step: output split must be a multiple of the 128-row tile");
+  MG_REQUIRE(n_split2 % 128 == 0 && n_split2 < N && (n_split2 == 0 || n_split2 > n_split), "fused decode step: bad second split");
   MegaLin L;
   L.N = N;
   L.n_split = n_split;
+  L.n_split2 = n_split2;
   L.K = K;
   L.tiles = (N + 127) / 128;
   L.num_kb = K / 64;

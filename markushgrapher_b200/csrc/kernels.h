@@ -128,7 +128,7 @@ struct MegaLin {           // a linear layer as a stream of pre-swizzled 32 KB (
   int tiles = 0, num_kb = 0;
   int kb_per_item = 0, ksplit = 0;  // work items = tiles * ksplit, item -> (tile = it / ksplit, k-slice = it % ksplit)
   int n_split = 0;  // two-output linears: rows [0, n_split) go to the first output, [n_split, N) to the second (0 = one output)
-  int pad_ = 0;
+  int n_split2 = 0; // three-segment linear (folded co|wi, -DMK_FOLD_FF): rows >= n_split2 read the SECOND activation source
 };
 struct MegaLayer {
   MegaLin lin[5];      // qkv|cq_x (ln1 / ln2 folded into the rows), o|cq_ctx, co, wi, wo -- decode_mega.cu phase table
@@ -146,6 +146,8 @@ struct MegaParams {
   float logit_scale, eps;
   int B, H, D, DFF, Mp, Tp;
   float *x, *qkv, *q, *ctx, *hbuf, *logits;
+  float* xalt = nullptr;  // -DMK_FOLD_FF: second residual-stream buffer (layer l reads X[l & 1], its wo phase writes the other)
+  float* dx = nullptr;    // -DMK_FOLD_FF: [B][D] Wco . ctx of the current layer (contiguous behind qkv: zeroed together)
   int ld_logits;
   float* part_val;
   int* part_idx;
@@ -170,7 +172,9 @@ struct MegaParams {
 };
 size_t mega_lin_bytes(int N, int K);
 // tiles the planes of one linear into dst (mega_lin_bytes(N, K) bytes) and fills the work split for n_ctas CTAs
-MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst, int n_split = 0);
+MegaLin make_mega_lin(cudaStream_t st, Planes w, int N, int K, int64_t ldk, bool store, int n_ctas, uint8_t* dst, int n_split = 0,
+                      int n_split2 = 0);
+bool mega_fold_ff();  // true if decode_mega.cu was built with -DMK_FOLD_FF (co folded into wi: 6 phases per layer)
 // finalize-time helpers of the folded cross query: dst[r][k] = src[r][k] * gain[k];  P[n][j] = sum_k A[n][k] * Bm[k][j] (fp64 accumulation)
 void launch_scale_cols(cudaStream_t st, const float* src, const float* gain, int rows, int K, float* dst);
 void launch_fold_product(cudaStream_t st, const float* A, const float* Bm, int N, int K, int J, float* P);

@@ -517,7 +517,9 @@ void mg_model::finalize(cudaStream_t st) {
       const int NL = c.num_decoder_layers, dff = c.d_ff;
       // phases 0 and 2 are two-output linears: [Wqkv diag(ln1); Wcq diag(ln2)] on x and [Wo; (Wcq diag(ln2)) Wo] on the
       // self-attention context together give the cross query (decode_mega.cu); built here from the fp32 weights
-      size_t per_layer = mega_lin_bytes(4 * d, d) + mega_lin_bytes(2 * d, d) + mega_lin_bytes(d, d) + mega_lin_bytes(dff, d) + mega_lin_bytes(d, dff);
+      const bool fold_ff = mega_fold_ff();  // co folded into wi: one three-segment linear [Wco; Wi' Wco; Wi'] of d + 2 dff rows
+      size_t per_layer = mega_lin_bytes(4 * d, d) + mega_lin_bytes(2 * d, d) + mega_lin_bytes(d, dff) +
+                         (fold_ff ? mega_lin_bytes(d + 2 * dff, d) : mega_lin_bytes(d, d) + mega_lin_bytes(dff, d));
       uint8_t* buf = own<uint8_t>((int64_t)(per_layer * NL + mega_lin_bytes(V, d)));
       mega_layers.resize(NL);
       auto tile = [&](const LinearW& W, bool store) {
@@ -525,15 +527,16 @@ void mg_model::finalize(cudaStream_t st) {
         buf += mega_lin_bytes(W.N, W.K);
         return L;
       };
-      float* fold = nullptr;  // [4d][d] fp32 scratch + planes of the same shape, freed below
+      float* fold = nullptr;  // [max(4d, d + 2 dff)][d] fp32 scratch + planes of the same shape, freed below
       bf16* fold_pl = nullptr;
       const int64_t ldk = rup(d, 8);
-      MG_CHECK_CUDA(cudaMalloc((void**)&fold, sizeof(float) * (size_t)4 * d * d));
-      MG_CHECK_CUDA(cudaMalloc((void**)&fold_pl, sizeof(bf16) * (size_t)2 * 4 * d * ldk));
-      const Planes fp{fold_pl, fold_pl + (int64_t)4 * d * ldk};
-      auto tile_fold = [&](int N, int n_split) {
+      const int64_t fold_rows = std::max<int64_t>(4 * d, fold_ff ? d + 2 * dff : 0);
+      MG_CHECK_CUDA(cudaMalloc((void**)&fold, sizeof(float) * (size_t)fold_rows * d));
+      MG_CHECK_CUDA(cudaMalloc((void**)&fold_pl, sizeof(bf16) * (size_t)2 * fold_rows * ldk));
+      const Planes fp{fold_pl, fold_pl + fold_rows * ldk};
+      auto tile_fold = [&](int N, int n_split, int n_split2 = 0) {
         launch_split(st, fold, N, d, d, fp, ldk);
-        MegaLin L = make_mega_lin(st, fp, N, d, ldk, false, mega_ctas, buf, n_split);
+        MegaLin L = make_mega_lin(st, fp, N, d, ldk, false, mega_ctas, buf, n_split, n_split2);
         buf += mega_lin_bytes(N, d);
         return L;
       };
@@ -553,7 +556,20 @@ void mg_model::finalize(cudaStream_t st) {
         launch_fold_product(st, fold + (int64_t)3 * d * d, need(p + "0.SelfAttention.o.weight").ptr, d, d, d, fold + (int64_t)d * d);
         MG_CHECK_CUDA(cudaMemcpyAsync(fold, need(p + "0.SelfAttention.o.weight").ptr, sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToDevice, st));
         M.lin[1] = tile_fold(2 * d, d);
-        M.lin[2] = tile(L.co, false); M.lin[3] = tile(L.wi, false); M.lin[4] = tile(L.wo, false);
+        if (fold_ff) {
+          // rows [0, d) = Wco; [d, d + dff) = (Wi diag(ln3)) Wco (fp64 accumulation); [d + dff, d + 2 dff) = Wi diag(ln3)
+          MG_REQUIRE(need(p + "1.EncDecAttention.o.weight").numel() == (int64_t)d * d &&
+                         need(p + "2.DenseReluDense.wi.weight").numel() == (int64_t)dff * d, "decoder co / wi weight shapes");
+          float* wi_s = fold + (int64_t)(d + dff) * d;
+          launch_scale_cols(st, need(p + "2.DenseReluDense.wi.weight").ptr, L.ln3, dff, d, wi_s);
+          launch_fold_product(st, wi_s, need(p + "1.EncDecAttention.o.weight").ptr, dff, d, d, fold + (int64_t)d * d);
+          MG_CHECK_CUDA(cudaMemcpyAsync(fold, need(p + "1.EncDecAttention.o.weight").ptr, sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToDevice, st));
+          M.lin[2] = tile_fold(d + 2 * dff, d, d + dff);
+          M.lin[3] = tile(L.wo, false);
+          M.lin[4] = M.lin[3];
+        } else {
+          M.lin[2] = tile(L.co, false); M.lin[3] = tile(L.wi, false); M.lin[4] = tile(L.wo, false);
+        }
         M.ln[0] = L.ln1; M.ln[1] = L.ln2; M.ln[2] = L.ln3;
         M.skb = M.svb = nullptr; M.ckv = nullptr; M.pad_ = nullptr;
       }
@@ -953,11 +969,12 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     sv[l] = a.get<float>((int64_t)B * Tp * d);
   }
   float* x = a.get<float>((int64_t)B * d);
-  float* qkv = a.get<float>((int64_t)B * 3 * d);
+  float* qkv = a.get<float>((int64_t)B * 4 * d);  // q | k | v, then (fused path with the folded FF) dx = Wco ctx behind them
   float* q = a.get<float>((int64_t)B * d);
   float* ctx = a.get<float>((int64_t)B * d);
   float* hbuf = a.get<float>((int64_t)B * c.d_ff);
   float* logits = a.get<float>((int64_t)B * Vld);
+  float* xalt = a.get<float>((int64_t)B * d);     // second residual buffer of the fused path (folded FF)
   const int n_part = (V + 127) / 128;  // LM-head tiles: per-tile (max, argmax) from the GEMM epilogue
   float* part_val = a.get<float>((int64_t)B * n_part);
   int* part_idx = a.get<int>((int64_t)B * n_part);
@@ -1018,7 +1035,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     ++launches;
   }
   // split-K accumulation buffers start at zero; afterwards each is re-zeroed by a later kernel of the chain
-  MG_CHECK_CUDA(cudaMemsetAsync(qkv, 0, sizeof(float) * (size_t)B * 3 * d, st));
+  MG_CHECK_CUDA(cudaMemsetAsync(qkv, 0, sizeof(float) * (size_t)B * 4 * d, st));
+  MG_CHECK_CUDA(cudaMemsetAsync(xalt, 0, sizeof(float) * (size_t)B * d, st));
   MG_CHECK_CUDA(cudaMemsetAsync(q, 0, sizeof(float) * (size_t)B * d, st));
   MG_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * (size_t)B * c.d_ff, st));
   if (nlanes == 2) {  // the second lane starts after the encoder, the K/V projection and the state reset
@@ -1042,6 +1060,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     mp.logit_scale = c.logit_scale; mp.eps = c.ln_eps;
     mp.B = B; mp.H = H; mp.D = d; mp.DFF = c.d_ff; mp.Mp = Mp; mp.Tp = Tp;
     mp.x = x; mp.qkv = qkv; mp.q = q; mp.ctx = ctx; mp.hbuf = hbuf; mp.logits = logits; mp.ld_logits = (int)Vld;
+    mp.xalt = xalt; mp.dx = qkv + (int64_t)B * 3 * d;
     mp.part_val = part_val; mp.part_idx = part_idx; mp.step_ptr = lanes[0].ctr; mp.mem_mask = mem_mask;
     mp.dec_bias = dec_bias; mp.lut = lut_dec; mp.bar_ctr = mega_bar;
     mp.rs = a.get<float>(3 * 32);
