@@ -407,7 +407,9 @@ def run_ours(args):
                        "images_per_gpu": B, "text_len": text_len, "max_length": args.max_length, "num_beams": nbeams,
                        "decode_steps_run": steps_run,
                        "parallelism": f"image-batch sharding x{world}" + (
-                           ", ncclAllGather of token ids per decode step" if world > 1 else ""),
+                           (", token ids of every decode step exchanged by NVLink peer stores fused into the selection kernel"
+                            if eng.dist_mode() == 2 and nbeams == 1 else ", ncclAllGather of token ids per decode step")
+                           if world > 1 else ""),
                        "l2": "inputs larger than L2 (cross-KV working set {:.1f} GB per step)".format(
                            B * L * 2 * M * d * 3 / 1e9)},
             "clocks": clocks,

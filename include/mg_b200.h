@@ -102,9 +102,17 @@ int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const
  * its GPU; the per-step all-gather carries the token of every image's best running beam plus the rank's "done" flag
  * (B_local + 1 int32), ranks whose search is over stay frozen until all are, and one final all-gather replaces the
  * provisional columns of all_ids with the finished sequences. B_local and max_length must be equal on all ranks: the call starts with a handshake
- * (one 2-int all-gather) and fails on every rank with a message naming the offending rank otherwise. */
+ * (one small all-gather) and fails on every rank with a message naming the offending rank otherwise.
+ *
+ * Greedy decoding moves the tokens WITHOUT a collective kernel when every rank can map every peer's memory (cudaIpc,
+ * NVLink / NVSwitch): the kernel that ends a decode step stores each image's token straight into an exchange buffer on
+ * every rank and raises a flag; an extra CTA of the next step's launch scatters the previous step's world x B_local
+ * tokens into all_ids and maintains the global stop counter, so ranks run at most two steps apart and stop together.
+ * MG_DIST=nccl (environment, read at mg_comm_init) or any rank failing to map a peer keeps the per-step ncclAllGather.
+ * mg_dist_mode: 0 single GPU, 1 NCCL all-gather per step, 2 peer stores. */
 int mg_nccl_unique_id(void* out_128_bytes);
 int mg_comm_init(mg_model* m, int world, int rank, const void* id_128_bytes);
+int mg_dist_mode(mg_model* m);
 int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64_t* input_ids, const float* bbox,
                      const float* pixel_values, const int64_t* attn_mask, int num_beams, int max_length, int64_t* all_ids,
                      int32_t* steps_run);

@@ -7,6 +7,8 @@
 // transformers/generation/utils.py::_sample (:2762-2805).
 #include <algorithm>
 
+#include <stdio.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -640,6 +642,43 @@ __device__ __forceinline__ bool argmax_better(float x, int xi, float best, int b
   if (xn || bn) return xn && (!bn || xi < bi);
   return x > best || (x == best && xi < bi);
 }
+// consumer half of the peer exchange: wait until every rank has published decode step `step`, then scatter the
+// world x B tokens into column step + 1 of the global id matrix and keep the global finished flags / unfinished count
+__device__ void peer_consume(const PeerExchange& px, int step) {
+  const int* mine = px.peers[px.rank];
+  const unsigned want = px.base + (unsigned)step + 1u;
+  const int ring = step % PX_RING;
+  if ((int)threadIdx.x < px.world) {
+    const unsigned* f = reinterpret_cast<const unsigned*>(mine) + ring * PX_MAXW + threadIdx.x;
+    unsigned v;
+    long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - want) >= 0) break;
+      if (clock64() - t0 > 20000000000LL) {  // a dead peer must not hang this GPU for ever
+        printf("peer exchange: rank %d never saw step %d of rank %d (flag %u, want %u)\n", px.rank, step, (int)threadIdx.x, v, want);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const int* slots = mine + PX_RING * PX_MAXW + (size_t)ring * px.world * px.bcap;
+  for (int i = threadIdx.x; i < px.world * px.B; i += blockDim.x) {
+    const int r = i / px.B, b = i - r * px.B;
+    const int tok = __ldcv(slots + (size_t)r * px.bcap + b);
+    px.all_ids[(int64_t)i * px.ld + step + 1] = tok;
+    if (!px.gfinished[i] && tok == px.eos) {
+      px.gfinished[i] = 1;
+      atomicSub(px.g_unfinished, 1);
+    }
+  }
+}
+__global__ void peer_drain_kernel(PeerExchange px, int step) { peer_consume(px, step); }
+void launch_peer_drain(cudaStream_t st, const PeerExchange& px, int step) {
+  peer_drain_kernel<<<1, 256, 0, st>>>(px, step);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
 __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ part_val,
                                                             const int* __restrict__ part_idx, int n_part,
                                                             const float* __restrict__ logits, int V, int64_t ld,
@@ -651,12 +690,23 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
                                                             int64_t dump_bs, int64_t dump_ss,
                                                             const int64_t* __restrict__ forced, int forced_ld,
                                                             int* __restrict__ step_tok,
-                                                            unsigned long long* __restrict__ step_ts) {
+                                                            unsigned long long* __restrict__ step_ts,
+                                                            const PeerExchange px) {
   const int b = blockIdx.x;
   griddep_launch();
   griddep_wait();
-  const float* lg = logits + (int64_t)b * ld;
   const int step = *step_ptr;
+  const int n_img = px.peers ? (int)gridDim.x - 1 : (int)gridDim.x;
+  if (b == n_img) {
+    // peer exchange: the extra CTA consumes the PREVIOUS step's tokens of all ranks.  It keeps its own launch counter
+    // (*step_ptr is advanced by the last image CTA of this very launch and may already show the next step)
+    const int k = *px.consumed;
+    if (k > 0) peer_consume(px, k - 1);
+    __syncthreads();
+    if (threadIdx.x == 0) *px.consumed = k + 1;
+    return;
+  }
+  const float* lg = logits + (int64_t)b * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   if (part_val) {  // per-tile maxima were produced by the LM-head epilogue: reduce n_part candidates
@@ -709,6 +759,10 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
     int tok = fin ? pad : bi;
     out_ids[(int64_t)b * out_ld + step + 1] = tok;
     if (step_tok) step_tok[b] = tok;
+    if (px.peers) {  // this image's token into slot (step % ring, my rank) of every rank's exchange buffer, over NVLink
+      const size_t off = PX_RING * PX_MAXW + ((size_t)(step % PX_RING) * px.world + px.rank) * px.bcap + b;
+      for (int r = 0; r < px.world; ++r) *reinterpret_cast<volatile int*>(px.peers[r] + off) = tok;
+    }
     if (forced) {
       // teacher forcing (model(**batch).logits): the next decoder input is given, nothing ever "finishes"
       tok = (int)forced[(int64_t)b * forced_ld + min(step + 1, forced_ld - 1)];
@@ -725,9 +779,17 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
   for (int c = threadIdx.x; c < D / 4; c += blockDim.x) x4[c] = e4[c];
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (px.peers) __threadfence_system(); else __threadfence();
     const int t = atomicAdd(ticket, 1);
-    if (t == (int)gridDim.x - 1) {
+    if (t == n_img - 1) {
+      if (px.peers) {  // all images of this rank are stored everywhere: raise this rank's flag on every rank
+        __threadfence_system();
+        const unsigned val = px.base + (unsigned)step + 1u;
+        for (int r = 0; r < px.world; ++r) {
+          unsigned* f = reinterpret_cast<unsigned*>(px.peers[r]) + (step % PX_RING) * PX_MAXW + px.rank;
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(val) : "memory");
+        }
+      }
       *ticket = 0;
       *step_ptr = step + 1;
       if (step_ts) {  // %globaltimer at the end of every decode step: true per-step latencies (mg_last_decode_p50)
@@ -744,11 +806,12 @@ void launch_greedy_select(cudaStream_t st, const float* part_val, const int* par
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
                           int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok,
-                          unsigned long long* step_ts) {
-  launch_pdl(greedy_select_kernel, dim3(B), dim3(256), (size_t)0, st, part_val, part_idx, n_part, logits, V, ld, emb, D,
-             eos, pad, out_ids, out_ld,
+                          unsigned long long* step_ts, const PeerExchange* px) {
+  const PeerExchange pe = px ? *px : PeerExchange{};
+  launch_pdl(greedy_select_kernel, dim3(B + (pe.peers ? 1 : 0)), dim3(256), (size_t)0, st, part_val, part_idx, n_part, logits,
+             V, ld, emb, D, eos, pad, out_ids, out_ld,
              finished, step_ptr, n_unfinished, ticket, x_next, logits_dump, dump_bs, dump_ss, forced, forced_ld,
-             step_tok, step_ts);
+             step_tok, step_ts, pe);
 }
 
 // decode state reset: ids[:,0] = start token, x = emb[start], finished = 0, step = 0

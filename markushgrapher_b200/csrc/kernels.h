@@ -58,12 +58,33 @@ void launch_kv24_roundtrip(cudaStream_t st, const float* kt, const float* v, int
 void launch_cross_attn_stream24(cudaStream_t st, const float* q, int B, int H, int D, const uint8_t* kv, int Mp,
                                 const int* mask, float* ctx);
 void launch_relu_split(cudaStream_t st, const float* x, int64_t n, Planes out);
+// Multi-GPU token exchange over NVLink peer memory, fused into the kernel that ends a decode step (decode.cu): every
+// rank owns one exchange buffer  [flags: PX_RING x PX_MAXW][slots: PX_RING x world x bcap]  mapped into all peers
+// (cudaIpc); greedy_select_kernel stores the step's token of each of its images into slot (step % PX_RING, rank) of
+// EVERY rank's buffer and then raises that rank's flag to base + step + 1; an extra CTA of the next step's launch
+// waits for all flags of the previous step and scatters the world x B tokens into the global id matrix (same stop
+// rule on every rank).  No collective kernel runs inside the decode loop.
+constexpr int PX_RING = 4;    // a rank can be at most two steps ahead of the slowest one (it waits for everyone's step s-1 in step s)
+constexpr int PX_MAXW = 64;   // ranks
+struct PeerExchange {
+  int* const* peers = nullptr;  // device array [world] of exchange-buffer bases (this rank's own included); null = off
+  int world = 1, rank = 0, bcap = 0, B = 0;
+  unsigned base = 0;            // flag epoch of this generate call
+  int64_t* all_ids = nullptr;   // (world * B, ld) global id matrix of this rank
+  int ld = 0, eos = 1;
+  int* gfinished = nullptr;     // [world * B]
+  int* g_unfinished = nullptr;
+  int* consumed = nullptr;      // launches of the consumer CTA so far in this generate call (device counter, starts at 0)
+};
+inline size_t peer_exchange_ints(int world, int bcap) { return (size_t)PX_RING * PX_MAXW + (size_t)PX_RING * world * bcap; }
+// consumes the tokens of decode step `step` (after the loop: the last one)
+void launch_peer_drain(cudaStream_t st, const PeerExchange& px, int step);
 // part_val/part_idx: optional [B][n_part] partial maxima from the LM-head epilogue (then `logits` is only dumped)
 void launch_greedy_select(cudaStream_t st, const float* part_val, const int* part_idx, int n_part, const float* logits, int B, int V, int64_t ld, const float* emb, int D,
                           int eos, int pad, int64_t* out_ids, int out_ld, int* finished, int* step_ptr,
                           int* n_unfinished, int* ticket, float* x_next, float* logits_dump, int64_t dump_bs,
                           int64_t dump_ss, const int64_t* forced, int forced_ld, int* step_tok,
-                          unsigned long long* step_ts = nullptr);
+                          unsigned long long* step_ts = nullptr, const PeerExchange* px = nullptr);
 void launch_scatter_step(cudaStream_t st, const int* gathered, int n_rows, int col, int ld, int eos, int64_t* all_ids,
                          int* gfinished, int* g_unfinished);
 void launch_decode_init(cudaStream_t st, const float* emb, int D, int start, int pad, int B, int64_t* out_ids,

@@ -192,6 +192,14 @@ struct mg_model {
   // multi-GPU (image-batch sharding): one NCCL all-gather of the step's token ids per decode step
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  // token exchange over NVLink peer memory (kernels.h PeerExchange): this rank's buffer, the peers' buffers mapped with
+  // cudaIpc, the device array of all bases; px_ok only if EVERY rank could map every peer (else: NCCL all-gather per step)
+  int* px_local = nullptr;
+  int** px_peers_dev = nullptr;
+  std::vector<void*> px_opened;
+  int px_bcap = 512;
+  bool px_ok = false;
+  unsigned px_calls = 0;
   int64_t* dist_all_ids = nullptr;  // (world*B, max_length) on every rank, set per call
   int* dist_chk = nullptr;          // [2 + 2*world] shard-shape handshake of mg_generate_dist
   // buffers of the last generate call (valid until the next encode/generate), for mg_profile_cross_attn
@@ -221,6 +229,7 @@ struct mg_model {
     if (aux_stream) cudaStreamDestroy(aux_stream);
     for (auto& e : lane_ev)
       if (e) cudaEventDestroy(e);
+    for (void* q : px_opened) cudaIpcCloseMemHandle(q);
     if (comm) nccl_api().CommDestroy(comm);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -1015,6 +1024,17 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     lanes[i].ctr = a.get<int>(8);
   }
 
+  // tokens travel through NVLink peer stores issued by the selection kernel itself when every rank mapped every peer
+  // at mg_comm_init (one micro-batch lane only); otherwise one ncclAllGather + scatter kernel per step
+  const bool p2p = dist && px_ok && B <= px_bcap && nlanes == 1;
+  PeerExchange px;
+  if (p2p) {
+    px.peers = px_peers_dev; px.world = world; px.rank = rank; px.bcap = px_bcap; px.B = B;
+    px.base = (px_calls++) * 8192u;
+    px.all_ids = dist_all_ids; px.ld = max_length; px.eos = c.eos_token_id;
+    px.gfinished = gfinished; px.g_unfinished = gctr + 3; px.consumed = gctr + 4;
+    MG_CHECK_CUDA(cudaMemsetAsync(gctr + 4, 0, sizeof(int), st));
+  }
   if (dist) {
     MG_CHECK_CUDA(cudaMemsetAsync(gfinished, 0, sizeof(int) * (size_t)world * B, st));
     MG_CHECK_CUDA(cudaMemsetAsync(dist_all_ids, 0, sizeof(int64_t) * (size_t)world * B * max_length, st));
@@ -1088,7 +1108,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       launch_decode_step(ls, mp, mega_ctas);
       launch_greedy_select(ls, part_val, part_idx, n_part, logits, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
                            ids_dev, max_length, finished, Ln.ctr, Ln.ctr + 1, Ln.ctr + 2, x,
-                           step_logits, (int64_t)(max_length - 1) * V, V, forced, forced_ld, step_tok, step_ts);
+                           step_logits, (int64_t)(max_length - 1) * V, V, forced, forced_ld, step_tok, step_ts,
+                           p2p ? &px : nullptr);
       launches += 2;
       return;
     }
@@ -1133,11 +1154,12 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
                          x + (int64_t)b0 * d,
                          step_logits ? step_logits + (int64_t)b0 * (max_length - 1) * V : nullptr,
                          (int64_t)(max_length - 1) * V, V, forced ? forced + (int64_t)b0 * forced_ld : nullptr,
-                         forced_ld, step_tok + b0, b0 == 0 ? step_ts : nullptr);
+                         forced_ld, step_tok + b0, b0 == 0 ? step_ts : nullptr, p2p ? &px : nullptr);
     launches += 1;
   };
   // one step of every lane; in multi-GPU mode followed by the exchange of the step's token ids
   auto exchange = [&](int col) {
+    if (p2p) return;  // already done by the step's selection kernel
     if (nlanes == 2) {  // the all-gather reads both lanes' tokens ...
       MG_CHECK_CUDA(cudaEventRecord(lane_ev[1], aux_stream));
       MG_CHECK_CUDA(cudaStreamWaitEvent(st, lane_ev[1], 0));
@@ -1234,6 +1256,10 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   if (nlanes == 2) {  // join the second lane back into the caller's stream
     MG_CHECK_CUDA(cudaEventRecord(lane_ev[1], aux_stream));
     MG_CHECK_CUDA(cudaStreamWaitEvent(st, lane_ev[1], 0));
+  }
+  if (p2p) {  // the last step's tokens of all ranks
+    launch_peer_drain(st, px, done_steps - 1);
+    ++launches;
   }
   MG_CHECK_CUDA(cudaEventRecord(ev_loop[1], st));
   if (out_len) {
@@ -1555,7 +1581,57 @@ int mg_comm_init(mg_model* m, int world, int rank, const void* id_128_bytes) {
   MG_CHECK_NCCL(nccl_api().CommInitRank(&m->comm, world, id, rank));
   m->world = world;
   m->rank = rank;
+  // ---- peer-memory token exchange: every rank exports its exchange buffer (cudaIpc) and maps everybody else's
+  const bool want_p2p = !(getenv("MG_DIST") && std::string(getenv("MG_DIST")) == "nccl") && world <= PX_MAXW;
+  {
+    const size_t n_int = peer_exchange_ints(world, m->px_bcap);
+    m->px_local = m->own<int>((int64_t)n_int);
+    MG_CHECK_CUDA(cudaMemset(m->px_local, 0, n_int * sizeof(int)));
+    char* xb = m->own<char>((int64_t)(sizeof(cudaIpcMemHandle_t) + 8) * (world + 1));
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;  // handle + "ok so far" flag
+    std::vector<char> mine(rec, 0), all(rec * world, 0);
+    int ok = want_p2p ? 1 : 0;
+    cudaIpcMemHandle_t h;
+    if (ok && cudaIpcGetMemHandle(&h, m->px_local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok) memcpy(mine.data(), &h, sizeof(h));
+    memcpy(mine.data() + sizeof(h), &ok, sizeof(int));
+    MG_CHECK_CUDA(cudaMemcpy(xb, mine.data(), rec, cudaMemcpyHostToDevice));
+    MG_CHECK_NCCL(nccl_api().AllGather(xb, xb + rec, rec, ncclChar, m->comm, nullptr));
+    MG_CHECK_CUDA(cudaMemcpy(all.data(), xb + rec, rec * world, cudaMemcpyDeviceToHost));
+    std::vector<int*> bases(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+      int okr;
+      memcpy(&okr, all.data() + r * rec + sizeof(h), sizeof(int));
+      ok = ok && okr;
+    }
+    for (int r = 0; r < world && ok; ++r) {
+      if (r == rank) { bases[r] = m->px_local; continue; }
+      cudaIpcMemHandle_t hr;
+      memcpy(&hr, all.data() + r * rec, sizeof(hr));
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      m->px_opened.push_back(q);
+      bases[r] = static_cast<int*>(q);
+    }
+    // second round: the mapping must have worked on EVERY rank, or all of them stay with the NCCL all-gather
+    MG_CHECK_CUDA(cudaMemcpy(xb, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    MG_CHECK_NCCL(nccl_api().AllGather(xb, xb + rec, sizeof(int), ncclChar, m->comm, nullptr));
+    std::vector<int> oks(world, 0);
+    MG_CHECK_CUDA(cudaMemcpy(oks.data(), xb + rec, sizeof(int) * world, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < world; ++r) ok = ok && oks[r];
+    if (ok) {
+      m->px_peers_dev = reinterpret_cast<int**>(m->own<int*>(world));
+      MG_CHECK_CUDA(cudaMemcpy(m->px_peers_dev, bases.data(), sizeof(int*) * world, cudaMemcpyHostToDevice));
+    }
+    m->px_ok = ok != 0;
+  }
   MG_API_END
+}
+
+int mg_dist_mode(mg_model* m) {
+  // 0 = single GPU, 1 = ncclAllGather of the token ids per decode step, 2 = NVLink peer stores fused into the selection kernel
+  if (!m || !m->comm) return 0;
+  return m->px_ok ? 2 : 1;
 }
 
 int mg_generate_dist(mg_model* m, void* stream, int B_local, int Lt, const int64_t* input_ids, const float* bbox,

@@ -209,6 +209,12 @@ class MGEngine:
             _lib.check(L.mg_comm_init(self._h, world, rank, box[0]), "mg_comm_init")
         self.world, self.rank = world, rank
 
+    def dist_mode(self) -> int:
+        """0 single GPU, 1 ncclAllGather of the token ids per decode step, 2 NVLink peer stores fused into the selection kernel"""
+        L = _lib.lib()
+        L.mg_dist_mode.argtypes = [ctypes.c_void_p]
+        return int(L.mg_dist_mode(self._h))
+
     def generate_dist(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512, num_beams=1):
         """this rank's shard in, ids of the WHOLE batch (world*B_local, max_length) out, on every rank"""
         ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)

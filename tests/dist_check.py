@@ -26,7 +26,31 @@ lo, hi = shard_range(n, world, rank)
 ids = eng.generate_dist(**{k: v[lo:hi] for k, v in inp.items()}, max_length=18).cpu()
 ref = oracle.generate_greedy(**inp, max_length=18)
 ok = torch.equal(ids[:, : ref.shape[1]], ref)
-print(f"rank {rank}/{world}: all-gathered ids {tuple(ids.shape)} match oracle for the whole batch: {ok}")
+print(f"rank {rank}/{world}: exchange mode {eng.dist_mode()} (2 = NVLink peer stores, 1 = ncclAllGather per step): "
+      f"ids {tuple(ids.shape)} match oracle for the whole batch: {ok}")
+# the other exchange path (the environment switch is read when the communicator is created)
+os.environ["MG_DIST"] = "nccl"
+eng_n = MGEngine(cfg, oracle.export_state(), device=torch.device("cuda", local))
+eng_n.comm_init_from_torch()
+del os.environ["MG_DIST"]
+ids_n = eng_n.generate_dist(**{k: v[lo:hi] for k, v in inp.items()}, max_length=18).cpu()
+okn = eng_n.dist_mode() == 1 and torch.equal(ids_n, ids)
+print(f"rank {rank}/{world}: exchange mode {eng_n.dist_mode()}: same ids as the peer-store path: {okn}")
+ok = ok and okn
+# early EOS: ranks' rows finish on different steps, all ranks must stop on the same step and pad alike
+import copy
+o3 = copy.deepcopy(oracle)
+with torch.no_grad():
+    o3.lm_head.weight[1] = sum(o3.lm_head.weight[r] for r in (7, 11, 13)) * 1.2
+eng3 = MGEngine(cfg, o3.export_state(), device=torch.device("cuda", local))
+eng3.comm_init_from_torch()
+inp3 = O.make_inputs(cfg, 3 * world, 14, seed=21)
+lo3, hi3 = shard_range(3 * world, world, rank)
+ids3 = eng3.generate_dist(**{k: v[lo3:hi3] for k, v in inp3.items()}, max_length=128).cpu()
+ref3 = o3.generate_greedy(**inp3, max_length=128)
+ok3 = torch.equal(ids3[:, : ref3.shape[1]], ref3) and bool((ids3[:, ref3.shape[1]:] == 0).all()) and eng3.last_steps < 127
+print(f"rank {rank}/{world}: early-EOS decode (oracle width {ref3.shape[1]}, steps run {eng3.last_steps}) matches: {ok3}")
+ok = ok and ok3
 # beam search, 4 beams: early-EOS made likely so that ranks finish their searches on different steps
 import copy
 o2 = copy.deepcopy(oracle)

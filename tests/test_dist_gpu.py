@@ -29,6 +29,7 @@ def test_single_rank_nccl_generate_matches_plain_generate():
     ref = oracle.generate_greedy(**inp, max_length=18)
     plain = eng.generate(**inp, max_length=18, trim=False)
     dist_ids = eng.generate_dist(**inp, max_length=18)
+    assert eng.dist_mode() == 2          # single rank: the peer-store exchange path (its own buffer is the only peer)
     assert torch.equal(dist_ids, plain)
     assert torch.equal(dist_ids.cpu()[:, : ref.shape[1]], ref)
     # beam search through the sharded entry (single rank): same ids as the plain call
