@@ -159,8 +159,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // griddep_wait(): block until the preceding kernel in the stream has completed and its writes are visible.
 // griddep_launch(): allow the next kernel (launched with the programmatic-serialization attribute) to start its
 // independent prologue (barrier init, TMEM alloc, weight / KV prefetch) while this one is still running.
+// -DMG_NO_GRIDDEP (diagnostic build, with MG_NO_PDL=1 at run time): compiles both out, e.g. to tell compute-sanitizer
+// synccheck reports about named barriers that follow launch_dependents (PREEXIT) from real divergence.
+#ifdef MG_NO_GRIDDEP
+__device__ __forceinline__ void griddep_wait() {}
+__device__ __forceinline__ void griddep_launch() {}
+#else
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ----------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ float warp_sum(float v) {

@@ -118,6 +118,21 @@ def test_activation_rows_33_to_128_vs_oracle(B):
     assert torch.equal(ids.cpu(), ids_ref)
 
 
+@pytest.mark.parametrize("B,nb", [(12, 5), (24, 5), (40, 4)])
+def test_beam_rows_33_to_160_vs_stock_beam_search(B, nb):
+    """beam search with more than 32 decoder rows (B x beams = 60 / 120 / 160: skinny_tc_kernel<2> / <4> and the
+    128-row launch split) and the kv24 cross K/V shared by an image's beams, against GenerationMixin._beam_search"""
+    cfg = O.MGConfig.small()
+    oracle = O.build(cfg, seed=0)
+    inp = O.make_inputs(cfg, B, 14, seed=300 + B, ragged=True)
+    ref = oracle.hf_generate(**inp, max_length=20, num_beams=nb)
+    eng = MGEngine(cfg, oracle.export_state())
+    ids = eng.generate(**inp, max_length=20, num_beams=nb)
+    eng.close()
+    assert ids.shape == ref.shape, (ids.shape, ref.shape)
+    assert torch.equal(ids.cpu(), ref)
+
+
 def test_full_size_batch128_equals_four_fused_batches(full_pair):
     """configs[3] shape (128 images per GPU) at the full dims: whatever path serves B = 128 must emit the ids of the
     same images decoded as four batches of 32 on the fused kernel; rows 0..1 are also checked against the oracle."""
