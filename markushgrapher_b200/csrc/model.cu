@@ -312,14 +312,22 @@ struct mg_model {
     size_t cap = 0;
     const void *k_ids = nullptr, *k_box = nullptr, *k_px = nullptr, *k_mask = nullptr;  // host pointers staged here
     int B = 0, Lt = 0;
-    bool valid = false;
+    bool valid = false;     // holds a staged batch that no generate call has consumed yet
+    uint64_t seq = 0;       // staging order (the older slot is recycled first)
     cudaEvent_t ready = nullptr;
     int64_t *d_ids = nullptr, *d_mask = nullptr, *d_out = nullptr;
     float *d_box = nullptr, *d_px = nullptr;
   };
   HostStage stage[2];
-  int stage_busy = -1;  // slot the running / last generate reads from
+  uint64_t stage_seq = 0;
   cudaStream_t copy_stream = nullptr;
+  // slot to stage the next batch into: one that holds no unconsumed batch, else the older one.  Calls are made from one
+  // thread and mg_generate_host returns only when its batch is done, so a slot without a pending batch is idle.
+  int pick_stage_slot() const {
+    if (!stage[0].valid) return 0;
+    if (!stage[1].valid) return 1;
+    return stage[0].seq <= stage[1].seq ? 0 : 1;
+  }
   // copies one batch of host inputs into slot `s` on stream `cs` (max_length sizes the ids-out buffer)
   void stage_inputs(HostStage& s, cudaStream_t cs, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
                     const int64_t* mask, int out_cols) {
@@ -347,6 +355,7 @@ struct mg_model {
     s.k_ids = ids; s.k_box = bbox; s.k_px = px; s.k_mask = mask;
     s.B = B; s.Lt = Lt;
     s.valid = true;
+    s.seq = ++stage_seq;
   }
 
   int64_t* ids_buf = nullptr;
@@ -1712,11 +1721,10 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
   if (slot >= 0) {
     MG_CHECK_CUDA(cudaStreamWaitEvent(st, m->stage[slot].ready, 0));
   } else {
-    slot = m->stage_busy == 0 ? 1 : 0;
+    slot = m->pick_stage_slot();
     m->stage_inputs(m->stage[slot], st, B, Lt, input_ids, bbox, pixel_values, attn_mask, max_length);
   }
   mg_model::HostStage& S = m->stage[slot];
-  m->stage_busy = slot;
   S.valid = false;  // consumed: a later call with the same host pointers copies again (the caller may have refilled them)
   int64_t* d_out = S.d_out;
   int rc = mg_generate(m, st, B, Lt, S.d_ids, S.d_box, S.d_px, attn_mask ? S.d_mask : nullptr, num_beams, max_length, d_out,
@@ -1745,7 +1753,7 @@ int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const
   MG_REQUIRE(m->finalized, "mg_finalize has not been called");
   MG_REQUIRE(B > 0 && Lt > 0 && max_length >= 2, "bad sizes");
   if (!m->copy_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-  const int slot = m->stage_busy == 0 ? 1 : 0;  // never the slot the running / last generate call reads
+  const int slot = m->pick_stage_slot();  // never a slot whose batch is still waiting for its generate call
   m->stage_inputs(m->stage[slot], m->copy_stream, B, Lt, input_ids, bbox, pixel_values, attn_mask, max_length);
   MG_API_END
 }

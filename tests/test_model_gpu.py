@@ -66,6 +66,22 @@ def test_generate_host_path(pair):
     assert torch.equal(ids, ids_ref)
 
 
+def test_prefetch_host_overlapped_staging(pair):
+    """mg_prefetch_host: the next batch's inputs travel on the copy stream while another batch decodes; batches are
+    matched by host pointer, unmatched calls stage inside the call, a prefetched batch is never overwritten"""
+    cfg, oracle, eng = pair
+    a = {k: v.pin_memory() for k, v in O.make_inputs(cfg, 2, 12, seed=3).items()}
+    b = {k: v.pin_memory() for k, v in O.make_inputs(cfg, 3, 12, seed=4).items()}
+    ref_a, ref_b = oracle.generate_greedy(**a, max_length=16), oracle.generate_greedy(**b, max_length=16)
+    eng.prefetch_host(**a, max_length=16)
+    eng.prefetch_host(**b, max_length=16)           # both slots hold a pending batch now
+    assert torch.equal(eng.generate_host(**a, max_length=16), ref_a)
+    eng.prefetch_host(**a, max_length=16)           # recycles a's slot, b stays staged
+    assert torch.equal(eng.generate_host(**b, max_length=16), ref_b)
+    assert torch.equal(eng.generate_host(**a, max_length=16), ref_a)
+    assert torch.equal(eng.generate_host(**b, max_length=16), ref_b)   # nothing staged: copies inside the call
+
+
 def test_drop_in_model_class_generate_and_logits():
     """the reference-facing object (MarkushgrapherForConditionalGeneration) end to end: generate() as called at
     utils_evaluation.py:279-285 and model(**batch).logits as called at curriculumTrainer.py:655"""
