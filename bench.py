@@ -380,6 +380,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     steps_run = eng.last_steps
+    m_enc, m_dec = eng.last_memory_len()
     if rank == 0:
         peak, peak_src = read_peaks()
         images = B * world * args.steps
@@ -387,7 +388,10 @@ def run_ours(args):
         e2e = images / (ms_e2e / 1000.0)
         ach = prof["bytes_per_launch"] / (prof["ms_per_launch"] * 1e-3) / 1e9 if prof else 0.0
         # decode-step HBM model: weights (hi+lo planes = 4 B/param) + B*(cross KV + self KV), fp32
-        d, L, M = cfg.d_model, cfg.num_decoder_layers, cfg.swin_tokens + text_len + cfg.n_patches
+        # M = memory positions the decoder holds K/V for: masked positions (patches absorbed by OCR tokens leave a padded
+        # tail, text padding) are dropped before the cross K/V projection -- they contribute exactly 0 -- so the
+        # ALGORITHMIC bytes of a step count the kept positions only (declared in config.memory_positions)
+        d, L, M = cfg.d_model, cfg.num_decoder_layers, m_dec
         # weights read by one step: q,k,v,o + cross q,o + wi,wo per layer (cross k,v run once per image, not per step)
         w_bytes = 4 * (L * (6 * d * d + 2 * d * cfg.d_ff) + cfg.vocab_size * d)
         # cross K/V: kv24 = 3 bytes per element (fp32 rounded to 24 significant bits); self K/V (mean cached length
@@ -406,6 +410,7 @@ def run_ours(args):
                                    f"{'greedy' if nbeams == 1 else 'beam=' + str(nbeams)} <={args.max_length} tok",
                        "images_per_gpu": B, "text_len": text_len, "max_length": args.max_length, "num_beams": nbeams,
                        "decode_steps_run": steps_run,
+                       "memory_positions": {"encoder": m_enc, "decoder_after_dropping_masked": m_dec},
                        "parallelism": f"image-batch sharding x{world}" + (
                            (", token ids of every decode step exchanged by NVLink peer stores fused into the selection kernel"
                             if eng.dist_mode() == 2 and nbeams == 1 else ", ncclAllGather of token ids per decode step")

@@ -131,6 +131,12 @@ int mg_forward_logits(mg_model* m, void* stream, int B, int Lt, const int64_t* i
  *   MG_MEGA_L2PF=<KB> bytes of the coming cross-attention phase each CTA of the fused kernel prefetches into L2
  *                    (default 384, 0 = off; timing only, results identical). */
 
+/* Memory lengths of the last generate call: M_encoder = swin tokens + text + patches (what mg_encode returns);
+ * M_decoder = positions the decoder actually holds K/V for.  Masked positions (text padding, the padded tail behind the
+ * surviving patches) contribute exp(finfo.min - max) = 0 to every cross-attention, so they are dropped before the cross
+ * K/V projection: valid rows in order, every image padded with masked rows to the batch maximum (rounded up to 8).
+ * Results are unchanged; the bytes streamed per generated token shrink accordingly.  MG_COMPACT=0 keeps all positions. */
+int mg_last_memory_len(mg_model* m, int32_t* M_encoder, int32_t* M_decoder);
 /* kernels this model has launched since mg_finalize (every entry point counts its own launches) */
 int mg_launch_count(mg_model* m, int64_t* kernels_launched);
 /* statistics of the last mg_generate call (host pointers, any may be NULL) */

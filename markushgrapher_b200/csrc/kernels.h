@@ -22,6 +22,10 @@ void launch_enc_softmax(cudaStream_t st, const float* scores, const uchar2* hv, 
                         int nbuckets, int B, int H, int Sp, Planes P);
 void launch_fill_f32(cudaStream_t st, float* p, int64_t n, float v);
 void launch_build_mem_mask(cudaStream_t st, const int* vtl_mask, int B, int Sp, int S, int n_sw, int Mp, int* out);
+// decoder-side compaction of the encoder memory (masked positions dropped, valid rows in order, padded to Mc per image)
+void launch_compact_plan(cudaStream_t st, const int* mask, int B, int Mp, int* src, int* n_valid);
+void launch_compact_gather(cudaStream_t st, const float* mem, const int* src, const int* n_valid, int B, int Mp, int Mc,
+                           int D, float* out, int* mask_out);
 
 // ---- enc_flash.cu: fused encoder self-attention (scores, bucketed bias, online softmax, P.V in one tcgen05 kernel)
 size_t enc_bias_code_bytes(int B, int Sp);

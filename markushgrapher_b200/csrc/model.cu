@@ -175,6 +175,12 @@ struct mg_model {
   float* mem = nullptr;   // [B, Mp, d]
   Planes mem_pl;          // planes of mem
   int* mem_mask = nullptr;  // [B, Mp]
+  // decoder-side view of the memory (valid rows only, padded to the batch maximum dMp; ops.cu compact_*): what the cross
+  // K/V projection and every decode kernel read.  Equal to mem / mem_pl / mem_mask / cur_Mp when MG_COMPACT=0.
+  float* dmem = nullptr;
+  Planes dmem_pl;
+  int* dmask = nullptr;
+  int dMp = 0, dM = 0;  // padded length, longest valid length
   int64_t launches = 0;
   float last_encode_ms = 0.f, last_decode_ms = 0.f;
   float last_loop_ms = 0.f;   // the decode-step loop alone (cross-KV projection excluded), CUDA events on the stream
@@ -395,6 +401,7 @@ struct mg_model {
                    const int64_t* amask);
   void project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv,
                         std::vector<uint8_t*>* ckv24 = nullptr);
+  void prepare_decoder_memory(cudaStream_t st, int B);
   void generate(cudaStream_t st, int B, int max_length, int64_t* out_ids, int32_t* out_len, float* step_logits,
                 int32_t* steps_run, const int64_t* forced = nullptr, int forced_ld = 0);
   void generate_beam(cudaStream_t st, int B, int nb, int max_length, int64_t* out_ids, int32_t* out_len,
@@ -915,10 +922,40 @@ void mg_model::encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const 
 // swap, V head-major [B][H][Mp][64]: every (image, head) block is one contiguous stream for the decode kernels.
 // With ckv24 the fp32 results of a layer are repacked into kv24 blocks (decode.cu: 3 bytes per element) and the two
 // fp32 buffers are reused by the next layer.
+// Drops the masked memory positions before anything decoder-side touches them (scratch arena; call after its reset).
+// One host read of B counters per generate call sizes the compacted length.
+void mg_model::prepare_decoder_memory(cudaStream_t st, int B) {
+  const int d = cfg.d_model;
+  const bool env_off = getenv("MG_COMPACT") && getenv("MG_COMPACT")[0] == '0';  // read per call (A/B, tests)
+  dmem = mem; dmem_pl = mem_pl; dmask = mem_mask; dMp = cur_Mp; dM = cur_M;
+  if (env_off) return;
+  Arena& a = scratch;
+  int* src = a.get<int>((int64_t)B * cur_Mp);
+  int* nv = a.get<int>(B);
+  launch_compact_plan(st, mem_mask, B, cur_Mp, src, nv);
+  ++launches;
+  std::vector<int> h(B);
+  MG_CHECK_CUDA(cudaMemcpyAsync(h.data(), nv, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  MG_CHECK_CUDA(cudaStreamSynchronize(st));
+  int mx = 1;
+  for (int v : h) mx = std::max(mx, v);
+  const int Mc = (int)rup(mx, 8);
+  if (Mc >= cur_Mp) return;  // nothing to drop
+  dM = mx;
+  dMp = Mc;
+  dmem = a.get<float>((int64_t)B * Mc * d);
+  dmask = a.get<int>((int64_t)B * Mc);
+  dmem_pl = planes(a, (int64_t)B * Mc * d);
+  launch_compact_gather(st, mem, src, nv, B, cur_Mp, Mc, d, dmem, dmask);
+  launch_split(st, dmem, (int64_t)B * Mc, d, d, dmem_pl, d);
+  launches += 2;
+}
+
 void mg_model::project_cross_kv(cudaStream_t st, int B, std::vector<float*>& ckt, std::vector<float*>& cv,
                                 std::vector<uint8_t*>* ckv24) {
   const mg_config& c = cfg;
-  const int d = c.d_model, H = c.num_heads, Mp = cur_Mp, NL = c.num_decoder_layers;
+  const int d = c.d_model, H = c.num_heads, Mp = dMp, NL = c.num_decoder_layers;
+  const Planes mem_pl = dmem_pl;  // (shadows the member: the decoder-side view)
   Arena& a = scratch;
   float *tmp_k = nullptr, *tmp_v = nullptr;
   if (ckv24) {
@@ -966,9 +1003,12 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   const mg_config& c = cfg;
   MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
   MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
-  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
+  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, NL = c.num_decoder_layers;
   Arena& a = scratch;
   a.reset();
+  prepare_decoder_memory(st, B);
+  const int Mp = dMp;
+  int* const mem_mask = dmask;  // (shadows the member: the decoder-side view)
   // fused persistent decode step (decode_mega.cu) whenever the batch fits one activation tile
   // cross K/V with 24 significant bits (3 bytes / element) unless MG_KV24=0
   const bool env_kv24 = !(getenv("MG_KV24") && getenv("MG_KV24")[0] == '0');
@@ -1310,10 +1350,13 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
   MG_REQUIRE(B == cur_B && mem != nullptr, "generate: encode must run first on the same batch");
   MG_REQUIRE(max_length >= 2 && max_length <= 4096, "max_length out of range");
   MG_REQUIRE(nb >= 2 && nb <= 8, "2 <= num_beams <= 8");
-  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, Mp = cur_Mp, NL = c.num_decoder_layers;
+  const int d = c.d_model, H = c.num_heads, V = c.vocab_size, NL = c.num_decoder_layers;
   const int R = B * nb;
   Arena& a = scratch;
   a.reset();
+  prepare_decoder_memory(st, B);
+  const int Mp = dMp;
+  int* const mem_mask = dmask;  // (shadows the member: the decoder-side view)
   const int Tp = (int)rup(max_length, 4);
   const int64_t Vld = rup(V, 4);
   // cross K/V as kv24 blocks (3 bytes / element, decode.cu) streamed once per IMAGE for all its beams, unless MG_KV24=0
@@ -1772,13 +1815,13 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
   const mg_config& c = m->cfg;
   // the production launch shape: one micro-batch lane (prof_bn images) per launch
   const int B = m->prof_bn > 0 ? m->prof_bn : m->cur_B;
-  const int d = c.d_model, H = c.num_heads, Mp = m->cur_Mp, NL = (int)m->prof_ckt.size();
+  const int d = c.d_model, H = c.num_heads, Mp = m->dMp, NL = (int)m->prof_ckt.size();
   auto pass = [&]() {
     for (int l = 0; l < NL; ++l) {
       if (m->prof_kv24)
-        launch_cross_attn_stream24(st, m->prof_q, B, H, d, m->prof_ckv[l], Mp, m->mem_mask, m->prof_ctx);
+        launch_cross_attn_stream24(st, m->prof_q, B, H, d, m->prof_ckv[l], Mp, m->dmask, m->prof_ctx);
       else
-        launch_cross_attn_stream(st, m->prof_q, B, H, d, m->prof_ckt[l], m->prof_cv[l], Mp, m->mem_mask, m->prof_ctx);
+        launch_cross_attn_stream(st, m->prof_q, B, H, d, m->prof_ckt[l], m->prof_cv[l], Mp, m->dmask, m->prof_ctx);
     }
   };
   pass();  // warm-up
@@ -1791,7 +1834,7 @@ int mg_profile_cross_attn(mg_model* m, void* stream, int reps, float* ms_per_lau
   if (ms_per_launch) *ms_per_launch = ms / (float)(reps * NL);
   // algorithmic bytes of one launch: K and V of the true memory length M (fp32), the mask, q in, ctx planes out
   if (bytes_per_launch)
-    *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->cur_M * d * (m->prof_kv24 ? 3 : 4) + (int64_t)m->cur_M * 4 +
+    *bytes_per_launch = (int64_t)B * ((int64_t)2 * m->dMp * d * (m->prof_kv24 ? 3 : 4) + (int64_t)m->dMp * 4 +
                                       (int64_t)d * 4 + (int64_t)d * (m->split2 ? 4 : 2));
   if (n_launches) *n_launches = reps * NL;
   MG_API_END
@@ -1818,6 +1861,14 @@ int mg_last_decode_loop(mg_model* m, float* loop_ms, int32_t* steps, int32_t* fu
   if (loop_ms) *loop_ms = m->last_loop_ms;
   if (steps) *steps = m->last_loop_steps;
   if (fused) *fused = m->last_fused;
+  MG_API_END
+}
+
+int mg_last_memory_len(mg_model* m, int32_t* M_encoder, int32_t* M_decoder) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (M_encoder) *M_encoder = m->cur_M;
+  if (M_decoder) *M_decoder = m->dMp;
   MG_API_END
 }
 

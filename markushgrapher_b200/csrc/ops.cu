@@ -479,4 +479,60 @@ void launch_build_mem_mask(cudaStream_t st, const int* vtl_mask, int B, int Sp, 
   MG_CHECK_CUDA(cudaGetLastError());
 }
 
+// =====================================================================================================
+// Decoder-side view of the encoder memory: masked positions (text padding, the padded tail behind the surviving
+// patches) never contribute to cross-attention -- exp(finfo.min - max) is exactly 0 in fp32 -- so they are dropped
+// BEFORE the cross K/V projection instead of being projected, stored and re-streamed once per generated token.
+// Valid rows keep their order (a softmax over keys does not depend on it anyway) and every image is padded with masked
+// rows to the batch maximum, so all decode kernels keep one uniform memory length.
+// plan: one CTA per image, src[b][k] = k-th valid position (stable), n_valid[b].
+__global__ void compact_plan_kernel(const int* __restrict__ mask, int Mp, int* __restrict__ src, int* __restrict__ n_valid) {
+  __shared__ int s_cnt[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int per = (Mp + 255) / 256;
+  const int lo = min(t * per, Mp), hi = min(lo + per, Mp);
+  int c = 0;
+  for (int i = lo; i < hi; ++i) c += mask[(int64_t)b * Mp + i] != 0;
+  s_cnt[t] = c;
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int i = 0; i < 256; ++i) {
+      const int v = s_cnt[i];
+      s_cnt[i] = run;
+      run += v;
+    }
+    n_valid[b] = run;
+  }
+  __syncthreads();
+  int k = s_cnt[t];
+  for (int i = lo; i < hi; ++i)
+    if (mask[(int64_t)b * Mp + i] != 0) src[(int64_t)b * Mp + k++] = i;
+}
+__global__ void compact_gather_kernel(const float* __restrict__ mem, const int* __restrict__ src,
+                                      const int* __restrict__ n_valid, int Mp, int Mc, int D, float* __restrict__ out,
+                                      int* __restrict__ mask_out) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  const bool ok = k < n_valid[b];
+  float4* o = reinterpret_cast<float4*>(out + ((int64_t)b * Mc + k) * D);
+  if (ok) {
+    const float4* in = reinterpret_cast<const float4*>(mem + ((int64_t)b * Mp + src[(int64_t)b * Mp + k]) * D);
+    for (int c = threadIdx.x; c < D / 4; c += blockDim.x) o[c] = in[c];
+  } else {
+    for (int c = threadIdx.x; c < D / 4; c += blockDim.x) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (threadIdx.x == 0) mask_out[(int64_t)b * Mc + k] = ok ? 1 : 0;
+}
+void launch_compact_plan(cudaStream_t st, const int* mask, int B, int Mp, int* src, int* n_valid) {
+  compact_plan_kernel<<<B, 256, 0, st>>>(mask, Mp, src, n_valid);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+void launch_compact_gather(cudaStream_t st, const float* mem, const int* src, const int* n_valid, int B, int Mp, int Mc,
+                           int D, float* out, int* mask_out) {
+  MG_REQUIRE(D % 4 == 0, "compact_gather: D must be a multiple of 4");
+  dim3 grid(Mc, B);
+  compact_gather_kernel<<<grid, 128, 0, st>>>(mem, src, n_valid, Mp, Mc, D, out, mask_out);
+  MG_CHECK_CUDA(cudaGetLastError());
+}
+
 }  // namespace mg

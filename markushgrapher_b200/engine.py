@@ -264,6 +264,14 @@ class MGEngine:
         return {"loop_ms": ms.value, "steps": n.value, "fused": bool(f.value), "step_p50_ms": p50.value,
                 "step_p99_ms": p99.value}
 
+    def last_memory_len(self):
+        """(encoder memory length, positions the decoder holds K/V for after dropping masked ones)"""
+        a, b = ctypes.c_int32(0), ctypes.c_int32(0)
+        L = _lib.lib()
+        L.mg_last_memory_len.argtypes = [ctypes.c_void_p] * 3
+        _lib.check(L.mg_last_memory_len(self._h, ctypes.addressof(a), ctypes.addressof(b)), "mg_last_memory_len")
+        return a.value, b.value
+
     def launch_count(self) -> int:
         k = ctypes.c_int64(0)
         L = _lib.lib()

@@ -82,6 +82,34 @@ def test_kernel_chain_path_token_identical_to_oracle(name):
         assert torch.equal(ids.cpu(), ids_ref), kv24
 
 
+@pytest.mark.parametrize("path", ["mega", "chain"])
+def test_masked_memory_positions_are_dropped_without_changing_results(path):
+    """ragged text (up to 3/4 of a row is padding) + patches absorbed by OCR tokens: the decoder-side memory keeps the
+    valid positions only (MG_COMPACT=0 keeps everything); ids identical, logits equal to fp32 reordering noise, both
+    equal to the oracle, for greedy and beam search"""
+    cfg = O.MGConfig.small()
+    oracle = O.build(cfg, seed=0)
+    inp = O.make_inputs(cfg, 5, 40, seed=61, ragged=True)
+    ids_ref, lg_ref = oracle.generate_greedy(**inp, max_length=24, return_logits=True)
+    beam_ref = oracle.hf_generate(**inp, max_length=20, num_beams=3)
+    out = {}
+    for compact in ("1", "0"):
+        with _env(MG_DECODE=path, MG_COMPACT=compact):
+            eng = MGEngine(cfg, oracle.export_state())
+            ids, lg = eng.generate(**inp, max_length=24, return_logits=True)
+            m_enc, m_dec = eng.last_memory_len()
+            beam = eng.generate(**inp, max_length=20, num_beams=3)
+            eng.close()
+        out[compact] = (ids.cpu(), lg.cpu(), beam.cpu(), m_enc, m_dec)
+    assert out["1"][3] == out["0"][3] and out["0"][4] >= out["0"][3]      # MG_COMPACT=0: every (padded) position kept
+    assert out["1"][4] < out["1"][3] - 8, out["1"][3:]                     # positions really dropped
+    assert torch.equal(out["1"][0], ids_ref) and torch.equal(out["0"][0], ids_ref)
+    assert torch.equal(out["1"][2], beam_ref) and torch.equal(out["0"][2], beam_ref)
+    d = (out["1"][1].double() - out["0"][1].double()).norm() / out["0"][1].double().norm()
+    assert d < 1e-5, d
+    assert ((out["1"][1].double() - lg_ref.double()).norm() / lg_ref.double().norm()) < 1e-3
+
+
 def test_full_size_batch32_paths_agree():
     """batch 32, full dims, 200 tokens: the fused kernel (148 CTAs, 4 concurrent items each), the kernel chain with
     kv24 and the kernel chain with fp32 cross K/V must emit the same token ids; the first two also agree on the
