@@ -230,6 +230,20 @@ class MGEngine:
         self.last_steps = steps.value
         return out
 
+    def generate_sharded(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512, num_beams=1):
+        """the WHOLE batch in (same tensors on every rank), ids of the whole batch (n, max_length) out on every rank:
+        contiguous shards (parallel.shard_range), padded to equal size because the library's exchange needs equal
+        shards, decoded through mg_generate_dist, padding rows dropped"""
+        from . import parallel
+
+        n = input_ids.shape[0]
+        lo, hi = parallel.shard_range(n, self.world, self.rank)
+        local = {"input_ids": input_ids[lo:hi], "bbox": bbox[lo:hi], "pixel_values": pixel_values[lo:hi],
+                 "attention_mask": None if attention_mask is None else attention_mask[lo:hi]}
+        local = parallel.pad_shard(local, parallel.shard_rows(n, self.world))
+        out = self.generate_dist(**local, max_length=max_length, num_beams=num_beams)
+        return parallel.unpad_gathered(out, n, self.world)
+
     def forward_logits(self, input_ids, bbox, pixel_values, decoder_input_ids, attention_mask=None):
         """teacher-forced logits (B, T, vocab) for decoder_input_ids (B, T) — `model(**batch).logits`"""
         ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)

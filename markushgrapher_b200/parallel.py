@@ -19,6 +19,35 @@ def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def shard_rows(n_items: int, world: int) -> int:
+    """rows every rank brings to the library's sharded generate (mg_generate_dist needs equal shards): the largest shard"""
+    return (n_items + world - 1) // world
+
+
+def pad_shard(local: dict, rows: int) -> dict:
+    """pads this rank's shard to `rows` images by repeating its last image (the padding rows are decoded and thrown
+    away by unpad_gathered); a rank whose shard is empty cannot be padded from its own rows"""
+    n = local["input_ids"].shape[0]
+    if n == rows:
+        return local
+    if n == 0:
+        raise ValueError("empty shard: fewer images than ranks (give every rank at least one image)")
+    out = {}
+    for k, v in local.items():
+        out[k] = None if v is None else torch.cat([v, v[-1:].expand(rows - n, *v.shape[1:])], dim=0).contiguous()
+    return out
+
+
+def unpad_gathered(all_ids: torch.Tensor, n_items: int, world: int) -> torch.Tensor:
+    """(world * rows, T) ids gathered from equal padded shards -> (n_items, T) in global image order"""
+    rows = shard_rows(n_items, world)
+    keep = []
+    for r in range(world):
+        lo, hi = shard_range(n_items, world, r)
+        keep.append(all_ids[r * rows: r * rows + (hi - lo)])
+    return torch.cat(keep, dim=0)
+
+
 def gather_token_ids(local_ids: torch.Tensor, n_total: int, pad_id: int = 0, group=None) -> torch.Tensor:
     """local_ids (b_local, T_local) int64 -> (n_total, T_max) on every rank, rows in global image order.
     Rows are right-padded with pad_id to the longest rank's width (ranks may stop at different steps)."""

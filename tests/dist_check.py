@@ -64,6 +64,14 @@ bref = o2.hf_generate(**inp2, max_length=40, num_beams=4)
 okb = torch.equal(bids[:, : bref.shape[1]], bref) and bool((bids[:, bref.shape[1]:] == 1).all())
 print(f"rank {rank}/{world}: beam-4 ids {tuple(bids.shape)} match stock beam search for the whole batch: {okb}")
 ok = ok and okb
+# a batch that does not divide by the ranks through the engine's shard / pad / unpad helper
+n_odd = 2 * world + 1
+inp_odd = O.make_inputs(cfg, n_odd, 12, seed=9)
+ids_odd = eng.generate_sharded(**inp_odd, max_length=18).cpu()
+ref_odd = oracle.generate_greedy(**inp_odd, max_length=18)
+ok_odd = ids_odd.shape[0] == n_odd and torch.equal(ids_odd[:, : ref_odd.shape[1]], ref_odd)
+print(f"rank {rank}/{world}: {n_odd} images over {world} ranks (padded shards): match oracle: {ok_odd}")
+ok = ok and ok_odd
 # unequal shards: every rank gets an error naming the offender
 if world > 1:
     from markushgrapher_b200._lib import MgError

@@ -19,6 +19,25 @@ def test_shard_range_covers_everything():
             assert got == list(range(n))
 
 
+def test_pad_and_unpad_equal_shards():
+    """the library's sharded generate needs equal shards: pad with the last image, drop the padding rows afterwards"""
+    from markushgrapher_b200.parallel import pad_shard, shard_rows, unpad_gathered
+
+    for n, world in ((7, 2), (9, 4), (8, 8), (5, 3)):
+        rows = shard_rows(n, world)
+        full = torch.arange(n)[:, None] * 10 + torch.arange(3)[None, :]            # "ids" of image i: 10 i + t
+        gathered = []
+        for r in range(world):
+            lo, hi = shard_range(n, world, r)
+            local = pad_shard({"input_ids": full[lo:hi], "attention_mask": None}, rows)
+            assert local["input_ids"].shape[0] == rows and local["attention_mask"] is None
+            assert torch.equal(local["input_ids"][hi - lo:], full[hi - 1: hi].expand(rows - (hi - lo), 3))
+            gathered.append(local["input_ids"])
+        assert torch.equal(unpad_gathered(torch.cat(gathered), n, world), full)
+    with pytest.raises(ValueError):
+        pad_shard({"input_ids": torch.zeros(0, 3)}, 1)
+
+
 def _fake_generate(input_ids, max_length, **kw):
     # deterministic stand-in for the engine: "decodes" row i to i, i+1, ... and stops rank-dependently
     b = input_ids.shape[0]
