@@ -40,8 +40,8 @@ constexpr int FA_OFF_V = FA_OFF_K + FA_KST * 2 * FA_K_BYTES;  // [VST][hi | lo]
 constexpr int FA_OFF_P = FA_OFF_V + FA_VST * 2 * FA_K_BYTES;  // [2 tiles][hi | lo]
 constexpr int FA_OFF_L1 = FA_OFF_P + 4 * FA_P_BYTES;          // float [2 * FA_MAXS]: 1-D bias of this head by j - i
 constexpr int FA_MAXS = 1664;                                 // max padded sequence (S <= 1536 + slack)
-constexpr int FA_OFF_TH = FA_OFF_L1 + 2 * FA_MAXS * 4;        // float [32] horizontal table of this head
-constexpr int FA_OFF_TV = FA_OFF_TH + 128;                    // float [32] vertical
+constexpr int FA_OFF_TH = FA_OFF_L1 + 2 * FA_MAXS * 4;        // float [33] horizontal table of this head, [32] = -inf (invisible key)
+constexpr int FA_OFF_TV = FA_OFF_TH + 256;                    // float [32] vertical
 constexpr int FA_OFF_BAR = FA_OFF_TV + 128;                   // mbarriers
 constexpr int FA_NBAR = 2 + 2 * FA_KST + 2 * FA_VST + 8 + 2 + 2 + 2;
 constexpr int FA_OFF_SLOT = FA_OFF_BAR + FA_NBAR * 8;
@@ -50,7 +50,8 @@ static_assert(FA_SMEM <= 227 * 1024, "shared memory budget");
 
 struct alignas(64) FlashParams {
   CUtensorMap tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo;
-  const uint16_t* code;   // [B][nqt * 128][nkb * 64]: (bh * 4) | (bv * 4) << 7 | visible << 15, tiled [qt][kb][i][j]
+  const uint16_t* code;   // [B][nqt * 128][nkb * 64], tiled [qt][kb][i][j]: low byte = bucket_h * 4 (128 = key invisible),
+                          // high byte = bucket_v * 4 -- both are byte offsets into the per-head tables
   const float *tab1d, *tabh, *tabv;  // [buckets][H]
   const int* lut1d;       // |j - i| -> bucket (without the sign offset)
   int lut1d_n, half_buckets;
@@ -95,6 +96,12 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+// 2^x, one MUFU (rel. error 2^-22; exp2f() adds a denormal-range rescale = 3 more instructions per score)
+__device__ __forceinline__ float fa_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -280,7 +287,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
         const int tt = threadIdx.x - 128;
         if (tt < 32) s_th[tt] = p.tabh[tt * p.H + h];
         else if (tt < 64) s_tv[tt - 32] = p.tabv[(tt - 32) * p.H + h];
-        for (int dd = tt; dd < 2 * p.Sp; dd += 256) {  // index dd = (j - i) + Sp
+        else if (tt == 64) s_th[32] = -INFINITY;  // invisible keys index this entry: their bias, hence their score, is -inf
+        for (int dd = tt; dd < 2 * p.Sp + 64; dd += 256) {  // index dd = (j - i) + Sp (finite for the padded keys too)
           int rel = dd - p.Sp;
           const int o1 = rel > 0 ? p.half_buckets : 0;
           rel = rel < 0 ? -rel : rel;
@@ -289,6 +297,25 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      // a warp whose 32 rows all lie past the sequence (the last item of an (image, head) is padded to 256 rows) only
+      // keeps the barrier protocol going: it leaves the issue slots of its scheduler to the warps with real rows
+      if (q256 * 256 + w * 128 + quad * 32 >= p.Sp) {
+        for (int kb = 0; kb < nkb; ++kb, ++n_blk) {
+          const uint32_t u = n_blk & 1u;
+          fa_wait(b_sfull + 8 * (2 * w + u), (n_blk >> 1) & 1u);
+          tc_fence_before();
+          fa_arrive(b_sempty + 8 * (2 * w + u));
+          if (kb > 0) {
+            fa_wait(b_pempty + 8 * w, n_pe & 1);
+            ++n_pe;
+          }
+          fa_arrive(b_pready + 8 * w);
+        }
+        fa_wait(b_pempty + 8 * w, n_pe & 1);
+        ++n_pe;
+        fa_arrive(b_ofree + 8 * w);
+        continue;
       }
       const uint16_t* code_row = p.code + ((size_t)b * p.nqt + (size_t)(i >> 7)) * (size_t)nkb * (128 * 64) + (size_t)(i & 127) * 64;
       uint4 cd[8];  // this row's 64 codes of the current block
@@ -325,9 +352,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
           for (int e = 0; e < 2; ++e) {
             const int c = 2 * c2 + e;
             const uint32_t cc = e ? (two >> 16) : (two & 0xffffu);
-            const float bias = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_tv) + ((cc >> 7) & 0x7cu)) +
-                               (*reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_th) + (cc & 0x7cu)) + l1[c]);
-            const float v = (cc & 0x8000u) ? s[c] + bias : -INFINITY;
+            (void)cc;
+            // the two code bytes ARE the table offsets (one PRMT each); an invisible key reads th[32] = -inf
+            const uint32_t oh = __byte_perm(two, 0u, e ? 0x4442 : 0x4440), ov = __byte_perm(two, 0u, e ? 0x4443 : 0x4441);
+            const float bias = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_tv) + ov) +
+                               (*reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_th) + oh) + l1[c]);
+            const float v = s[c] + bias;
             s[c] = v;
             bm = fmaxf(bm, v);
           }
@@ -344,7 +374,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
         bool moved = false;
         if (bm > m_ref + p.rescale_gap || m_ref == -INFINITY) {
           if (bm != -INFINITY) {
-            scale_o = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - bm) * LOG2E);
+            scale_o = (m_ref == -INFINITY) ? 0.f : fa_ex2((m_ref - bm) * LOG2E);
             sum *= scale_o;
             m_ref = bm;
             moved = true;
@@ -354,7 +384,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
         float bsum = 0.f;
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          s[c] = exp2f(fmaf(s[c], LOG2E, mneg));  // -inf -> 0
+          s[c] = fa_ex2(fmaf(s[c], LOG2E, mneg));  // -inf -> 0
           bsum += s[c];
         }
         sum += bsum;
@@ -446,8 +476,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
 // Horizontal / vertical relative-position buckets (RelativePositionBiasHorizontal / Vertical :935-970,
 // get_relative_position :887-895, bucket :466-512) + key visibility, ONCE per forward, shared by all layers / heads:
 //   pos = (b0 + b2) / 2 (float64);  rel = ((pos_j - pos_i) * 100).long();  bucket = (rel > 0) * 16 + lut[min(|rel|, cap)]
-// code = (bucket_h * 4) | (bucket_v * 4) << 7 | visible_j << 15, tiled [b][i / 128][j / 64][i % 128][j % 64] so that the
-// 64 codes a softmax thread needs for one key block are one 128-byte line.
+// code: low byte = bucket_h * 4, or 128 if key j is invisible; high byte = bucket_v * 4 (byte offsets into the per-head
+// tables), tiled [b][i / 128][j / 64][i % 128][j % 64] so that the 64 codes a softmax thread needs for one key block are
+// one 128-byte line.
 __global__ void enc_bias_code_kernel(const double* __restrict__ bbox_ext, const int* __restrict__ mask, int Sp, int nqt,
                                      int nkb, const int* __restrict__ lut_hv, int lut_n, int half_buckets,
                                      double scaling, uint16_t* __restrict__ code) {
@@ -468,9 +499,12 @@ __global__ void enc_bias_code_kernel(const double* __restrict__ bbox_ext, const 
       ry = ry < 0 ? -ry : ry;
       if (rx > lut_n - 1) rx = lut_n - 1;
       if (ry > lut_n - 1) ry = lut_n - 1;
-      c = (uint16_t)(((ox + lut_hv[rx]) << 2) | ((oy + lut_hv[ry]) << 9) | (mask[(int64_t)b * Sp + j] ? 0x8000 : 0));
+      const int vis = mask[(int64_t)b * Sp + j] != 0;
+      c = (uint16_t)((vis ? ((ox + lut_hv[rx]) << 2) : 128) | ((oy + lut_hv[ry]) << 10));
     } else if (j < Sp) {
-      c = (uint16_t)(mask[(int64_t)b * Sp + j] ? 0x8000 : 0);  // rows past the sequence: finite scores, never stored
+      c = (uint16_t)(mask[(int64_t)b * Sp + j] ? 0 : 128);  // rows past the sequence: finite scores, never stored
+    } else {
+      c = 128;                                               // keys past the sequence: invisible
     }
     out[(size_t)(j >> 6) * (128 * 64) + (j & 63)] = c;
   }

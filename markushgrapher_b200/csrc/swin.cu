@@ -368,7 +368,10 @@ struct alignas(64) WinAttnParams {
   int C, heads, ws, Hs, Ws, shift;
 };
 
-__global__ void __launch_bounds__(WA_WARPS * 32) window_attn_mma_kernel(const __grid_constant__ WinAttnParams p) {
+// MINB = CTAs per SM the register allocation aims at: 1 -> 154 registers, no spills; 2 -> 96 registers, ~300 bytes of
+// spills but twice the warps to hide the TMA / LDS / MMA latencies behind (A/B: MG_SWIN_MINB)
+template <int MINB>
+__global__ void __launch_bounds__(WA_WARPS * 32, MINB) window_attn_mma_kernel(const __grid_constant__ WinAttnParams p) {
   extern __shared__ uint8_t smw_raw[];
   uint8_t* const sm = smw_raw + ((1024u - (smem_u32(smw_raw) & 1023u)) & 1023u);
   float* const sq = reinterpret_cast<float*>(sm);                  // [144][32] swizzled
@@ -541,10 +544,15 @@ void launch_window_attn(cudaStream_t st, const float* qkv, const float* table, i
     const size_t smem = 1024 + (size_t)(3 * WA_T * 32 + 23 * 23) * 4 + 2 * WA_T * 4 + 64;
     static bool attr2 = false;
     if (!attr2) {
-      MG_CHECK_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MG_CHECK_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MG_CHECK_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       attr2 = true;
     }
-    window_attn_mma_kernel<<<(unsigned)(n_windows * heads), WA_WARPS * 32, smem, st>>>(p);
+    static const int minb = getenv("MG_SWIN_MINB") ? atoi(getenv("MG_SWIN_MINB")) : 2;
+    if (minb >= 2)
+      window_attn_mma_kernel<2><<<(unsigned)(n_windows * heads), WA_WARPS * 32, smem, st>>>(p);
+    else
+      window_attn_mma_kernel<1><<<(unsigned)(n_windows * heads), WA_WARPS * 32, smem, st>>>(p);
     MG_CHECK_CUDA(cudaGetLastError());
     return;
   }
