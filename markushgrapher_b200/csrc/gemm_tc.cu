@@ -564,7 +564,10 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
       if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
     }
-  } else if (warp >= 6) {
+  } else {
+  // warps 2..9 meet at ONE named barrier (row scales published by the statistic warps before the workers' epilogue);
+  // both groups reach it through the same instruction, which is also what compute-sanitizer synccheck expects
+  if (warp >= 6) {
     // ---------------------------------------------------------------- statistic warps (6..9, 128 threads)
     // RMSNorm row statistic over the FULL row, computed concurrently with the activation staging of the worker
     // warps (it used to follow it: +2.2 us on the critical path of every RMSNorm-fused linear)
@@ -599,8 +602,6 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
     } else {
       if (t < R) s_rs[t] = p.scale;
     }
-    __syncwarp();
-    asm volatile("bar.sync 3, 256;" ::: "memory");
   } else {
     // ---------------------------------------------------------------- workers (warps 2..5, 128 threads)
     const int t = threadIdx.x - 64;
@@ -668,8 +669,11 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
       for (int64_t i = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + t; i < n4; i += nthreads)
         z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncwarp();
-    asm volatile("bar.sync 3, 256;" ::: "memory");  // row scales s_rs[] published by the statistic warps
+  }
+  __syncwarp();
+  asm volatile("bar.sync 3, 256;" ::: "memory");  // row scales s_rs[] published by the statistic warps
+  if (warp < 6) {
+    const int t = threadIdx.x - 64;
     // ---------------------------------------------------------------- epilogue
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -727,6 +731,7 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
         p.amax_idx[(int64_t)t * gridDim.x + blockIdx.x] = bi;
       }
     }
+  }
   }
   tc_fence_before();
   __syncthreads();
