@@ -103,16 +103,6 @@ __device__ __forceinline__ float fa_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 16-byte read-only load that does not displace the K / V / Q tiles in L2: the bias codes are re-read once per head
-// (1.2 GB per layer at batch 32 -- no cache holds them between heads) whereas a (image, head)'s K / V are re-read by the
-// CTA's next four items within microseconds
-__device__ __forceinline__ uint4 fa_ldg_stream(const uint4* p, uint64_t policy) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p), "l"(policy));
-  return r;
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __grid_constant__ FlashParams p) {
@@ -282,8 +272,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t n_blk = 0, n_pe = 0, it_n = 0;
     constexpr float LOG2E = 1.4426950408889634f;
-    uint64_t pol_stream;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    // (measured: streaming the codes with L1::no_allocate + an L2 evict-first policy is SLOWER -- encoder 109.9 ->
+    // 123.6 ms per batch: a thread reads its 128-byte code line with eight 16-byte loads, and without the L1 allocation
+    // each of them goes to L2; plain read-only loads stay)
     uint8_t* const p_hi = sm + FA_OFF_P + (2 * w) * FA_P_BYTES + t * 128;
     uint8_t* const p_lo = p_hi + FA_P_BYTES;
     int h_tab = -1;  // head whose tables are in shared memory
@@ -334,7 +325,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
       {
         const uint4* src = reinterpret_cast<const uint4*>(code_row);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) cd[v] = fa_ldg_stream(src + v, pol_stream);
+        for (int v = 0; v < 8; ++v) cd[v] = __ldg(src + v);
       }
       float m_ref = -INFINITY, sum = 0.f;
       for (int kb = 0; kb < nkb; ++kb, ++n_blk) {
@@ -378,7 +369,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
         if (kb + 1 < nkb) {
           const uint4* src = reinterpret_cast<const uint4*>(code_row + (size_t)(kb + 1) * (128 * 64));
 #pragma unroll
-          for (int v = 0; v < 8; ++v) cd[v] = fa_ldg_stream(src + v, pol_stream);
+          for (int v = 0; v < 8; ++v) cd[v] = __ldg(src + v);
         }
         // ---- running maximum, lazily updated: the reference point only moves when the maximum grew by > 2^11 (the
         // probabilities of a block then reach at most 2048: no overflow, and the accumulator is rarely rescaled)
