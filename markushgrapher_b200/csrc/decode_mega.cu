@@ -1156,7 +1156,34 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
         // ------------------------------------------------------------------------------------ grid barrier
         cons_sync();
         bar_target += (unsigned)G;
+#ifdef MK_FLAGBAR
+        // experiment build (-DMK_FLAGBAR): no atomics on one word -- every CTA publishes its arrival with a plain store to
+        // its own flag, and one warp per CTA polls all flags with five coalesced loads per round
+        if (cw == 0) {
+          const unsigned epoch = (unsigned)step * (unsigned)(NL * MK_NPH) + (unsigned)phase_i + 1u;
+          volatile unsigned* const flags = p.bar_ctr + 4;
+          if (lane == 0) {
+            __threadfence();
+            flags[g] = epoch;
+          }
+          const long long t0 = clock64();
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const int idx = lane + 32 * i;
+              if (idx < G) ok = ok && (int)(flags[idx] - epoch) >= 0;
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (clock64() - t0 > 4000000000LL) mk_die(3, epoch, (uint32_t)g);
+          }
+          __threadfence();
+          if (lane == 0) MK_FLAG_ST(s_phase, phase_i + 1);
+        }
+        if (false) {
+#else
         if (ct == 0) {
+#endif
 #ifdef MK_FINE
           unsigned long long* ps = p.prof ? p.prof + ((size_t)g * 512 + phase_i) * 2 : nullptr;
 #endif

@@ -603,8 +603,8 @@ void mg_model::finalize(cudaStream_t st) {
       MG_CHECK_CUDA(cudaFree(fold_pl));
       mega_lm = tile(lm_head, true);
       mega_layers_dev = own<MegaLayer>(NL);
-      mega_bar = own<unsigned>(4);
-      MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, 4 * sizeof(unsigned), st));
+      mega_bar = own<unsigned>(4 + 256);  // [2] barrier counters (+2 spare), then one arrival flag per CTA (-DMK_FLAGBAR build)
+      MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, (4 + 256) * sizeof(unsigned), st));
     }
   }
   MG_CHECK_CUDA(cudaMallocHost((void**)&pinned_flag, 64));
@@ -1123,7 +1123,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       mega_layers[l].pad_ = nullptr;
     }
     MG_CHECK_CUDA(cudaMemcpyAsync(mega_layers_dev, mega_layers.data(), sizeof(MegaLayer) * NL, cudaMemcpyHostToDevice, st));
-    MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, 4 * sizeof(unsigned), st));
+    MG_CHECK_CUDA(cudaMemsetAsync(mega_bar, 0, (4 + 256) * sizeof(unsigned), st));
     MG_CHECK_CUDA(cudaStreamSynchronize(st));  // pageable source
     mp.layers = mega_layers_dev; mp.NL = NL; mp.lm_head = mega_lm; mp.final_ln = dec_final_ln;
     mp.logit_scale = c.logit_scale; mp.eps = c.ln_eps;
