@@ -58,6 +58,9 @@ struct alignas(64) FlashParams {
   bf16 *out_hi, *out_lo;  // ctx planes [B * Sp][D]
   int B, H, D, Sp, nkb, nq256, nqt;
   float rescale_gap;      // the running maximum's reference point moves only when the maximum grew by more than this
+  int opt;                // bit 0: bias codes loaded with an L2 evict-first policy (they are re-read once per head and must
+                          // not push the K / V tiles out of L2); bit 1: L2 prefetch of the code line two key blocks ahead;
+                          // bit 2: the producer prefetches the K / V blocks two ahead of the ring into L2
 };
 
 // bounded mbarrier wait: a protocol error becomes a trap (launch failure) instead of a hung GPU
@@ -86,6 +89,11 @@ __device__ __forceinline__ void fa_tma_3d(uint32_t dst, const CUtensorMap* m, ui
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(0)
       : "memory");
 }
+__device__ __forceinline__ void fa_tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(0)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -102,6 +110,15 @@ __device__ __forceinline__ float fa_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 16-byte read-only load with an L2 eviction-priority hint (L1 allocation as usual: a thread reads its 128-byte code
+// line with eight of these)
+__device__ __forceinline__ uint4 fa_ldg_hint(const uint4* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -173,6 +190,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
           fa_tma_3d(sm_a + FA_OFF_Q + (2 * w + 1) * FA_Q_BYTES, &p.tq_lo, b_qfull, h * 64, q256 * 256 + w * 128, b);
         }
         for (int kb = 0; kb < nkb; ++kb) {
+          if ((p.opt & 4) && kb + 2 < nkb) {  // L2 prefetch of the K / V blocks two ahead of the ring
+            fa_tma_prefetch_3d(&p.tk_hi, p.D + h * 64, (kb + 2) * FA_KB, b);
+            fa_tma_prefetch_3d(&p.tk_lo, p.D + h * 64, (kb + 2) * FA_KB, b);
+            fa_tma_prefetch_3d(&p.tv_hi, (kb + 2) * FA_KB, h * 64, b);
+            fa_tma_prefetch_3d(&p.tv_lo, (kb + 2) * FA_KB, h * 64, b);
+          }
           fa_wait(b_kempty + 8 * ks, kph ^ 1);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_kfull + 8 * ks), "r"(2 * FA_K_BYTES) : "memory");
           fa_tma_3d(sm_a + FA_OFF_K + (2 * ks) * FA_K_BYTES, &p.tk_hi, b_kfull + 8 * ks, p.D + h * 64, kb * FA_KB, b);
@@ -274,7 +297,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
     constexpr float LOG2E = 1.4426950408889634f;
     // (measured: streaming the codes with L1::no_allocate + an L2 evict-first policy is SLOWER -- encoder 109.9 ->
     // 123.6 ms per batch: a thread reads its 128-byte code line with eight 16-byte loads, and without the L1 allocation
-    // each of them goes to L2; plain read-only loads stay)
+    // each of them goes to L2)
+    uint64_t pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    const bool code_first = (p.opt & 1) != 0, code_pf = (p.opt & 2) != 0;
     uint8_t* const p_hi = sm + FA_OFF_P + (2 * w) * FA_P_BYTES + t * 128;
     uint8_t* const p_lo = p_hi + FA_P_BYTES;
     int h_tab = -1;  // head whose tables are in shared memory
@@ -324,8 +350,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
       uint4 cd[8];  // this row's 64 codes of the current block
       {
         const uint4* src = reinterpret_cast<const uint4*>(code_row);
+        if (code_first) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) cd[v] = __ldg(src + v);
+          for (int v = 0; v < 8; ++v) cd[v] = fa_ldg_hint(src + v, pol_first);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) cd[v] = __ldg(src + v);
+        }
+        if (code_pf && nkb > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(code_row + (size_t)(128 * 64)));
       }
       float m_ref = -INFINITY, sum = 0.f;
       for (int kb = 0; kb < nkb; ++kb, ++n_blk) {
@@ -368,8 +400,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) enc_flash_attn_kernel(const __g
         // next block's codes: the loads fly during the exponentials below
         if (kb + 1 < nkb) {
           const uint4* src = reinterpret_cast<const uint4*>(code_row + (size_t)(kb + 1) * (128 * 64));
+          if (code_first) {
 #pragma unroll
-          for (int v = 0; v < 8; ++v) cd[v] = __ldg(src + v);
+            for (int v = 0; v < 8; ++v) cd[v] = fa_ldg_hint(src + v, pol_first);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) cd[v] = __ldg(src + v);
+          }
+          if (code_pf && kb + 3 < nkb) asm volatile("prefetch.global.L2 [%0];" ::"l"(code_row + (size_t)(kb + 3) * (128 * 64)));
         }
         // ---- running maximum, lazily updated: the reference point only moves when the maximum grew by > 2^11 (the
         // probabilities of a block then reach at most 2048: no overflow, and the accumulator is rarely rescaled)
@@ -554,6 +592,8 @@ void launch_enc_flash_attn(cudaStream_t st, Planes qk, Planes vt, const uint16_t
   // MG_FLASH_GAP=<natural-log units>: test hook, 0 rescales the TMEM accumulator on every growth of the row maximum
   static const float gap = getenv("MG_FLASH_GAP") ? (float)atof(getenv("MG_FLASH_GAP")) : 11.f * 0.6931471805599453f;
   p.rescale_gap = gap;
+  static const int opt = getenv("MG_FLASH_OPT") ? atoi(getenv("MG_FLASH_OPT")) : 0;  // A/B switch, see FlashParams::opt
+  p.opt = opt;
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
