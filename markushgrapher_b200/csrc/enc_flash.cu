@@ -592,7 +592,9 @@ void launch_enc_flash_attn(cudaStream_t st, Planes qk, Planes vt, const uint16_t
   // MG_FLASH_GAP=<natural-log units>: test hook, 0 rescales the TMEM accumulator on every growth of the row maximum
   static const float gap = getenv("MG_FLASH_GAP") ? (float)atof(getenv("MG_FLASH_GAP")) : 11.f * 0.6931471805599453f;
   p.rescale_gap = gap;
-  static const int opt = getenv("MG_FLASH_OPT") ? atoi(getenv("MG_FLASH_OPT")) : 0;  // A/B switch, see FlashParams::opt
+  // A/B switch, see FlashParams::opt.  Encoder ms per batch of 32 on one box (gpurun_out/r2k_enc_opt*.log): 0: 113.4,
+  // 1: 112.3, 2: 112.0, 3: 110.9, 4: 112.2, 5: 112.2, 7: 110.7 -> evict-first codes + code prefetch by default
+  static const int opt = getenv("MG_FLASH_OPT") ? atoi(getenv("MG_FLASH_OPT")) : 3;
   p.opt = opt;
   static int n_sm = 0;
   if (!n_sm) {
