@@ -93,6 +93,29 @@ int mg_generate_host(mg_model* m, void* stream, int B, int Lt, const int64_t* in
 int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const float* bbox, const float* pixel_values,
                      const int64_t* attn_mask, int max_length);
 
+/* Encoder run-ahead (throughput mode for a stream of batches): queues the ENCODER of the NEXT batch (Swin, projector,
+ * VTL encoder -- the tensor-core-bound part) on a small SM partition of its own (CUDA green contexts, 16 SMs by
+ * default: MG_AHEAD_SMS; MG_AHEAD=0 disables) and returns at once.  The mg_generate / mg_generate_dist call that later
+ * passes the very same device pointers (contents unchanged in between) takes the finished encoder memory instead of
+ * encoding; a generate call made while another batch is being encoded ahead runs its decode loop -- HBM-bound, the
+ * tensor cores idle -- on the remaining SMs, so the two overlap.  `stream`: the work is ordered after what is queued
+ * there (the inputs).  *armed (may be NULL) = 1 if the encoder was queued, 0 if SM partitioning is unavailable (then
+ * nothing happens and the later generate call encodes as usual).  Results are identical either way.
+ * The reference has no counterpart: its evaluation loop encodes and decodes one batch at a time
+ * (markushgrapher/utils/ocsr/utils_evaluation.py:262-285). */
+int mg_encode_ahead(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                    const float* pixel_values, const int64_t* attn_mask, int32_t* armed);
+/* Same for HOST inputs: mg_prefetch_host + run-ahead encoder on the staged copy; consumed by the mg_generate_host call
+ * that passes the same host pointers. */
+int mg_encode_ahead_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                         const float* pixel_values, const int64_t* attn_mask, int max_length, int32_t* armed);
+/* After a generate call that took a run-ahead batch: the encoder's duration on its partition (ms, 0 if the call encoded
+ * itself) and the SM counts of the two partitions (0 if unavailable). */
+int mg_last_ahead(mg_model* m, float* encoder_ms, int32_t* sms_encoder, int32_t* sms_decoder);
+/* Waits for a run-ahead encoder still in flight and drops every batch that no generate call has taken (end of a stream
+ * of batches: later generate calls use all SMs again). */
+int mg_ahead_reset(mg_model* m);
+
 /* ---- multi-GPU: image-batch sharding, one process per GPU, one NCCL all-gather of token ids per decode step ----
  * mg_nccl_unique_id: rank 0 obtains a 128-byte NCCL id (host buffer) and ships it to the other ranks by any means
  * (bench.py uses torch.distributed). mg_comm_init: every rank joins. mg_generate_dist: like mg_generate on this rank's

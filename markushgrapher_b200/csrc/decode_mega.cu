@@ -31,6 +31,8 @@
 // gemm_tc.cu (UdopLayerNorm :333-355, UdopAttention :431-622 incl. compute_bias :514-529, UdopLayerFF :412-427,
 // decoder UdopStack :1146-1256, lm head :1585-1590); the selection stays in greedy_select_kernel.
 #include <algorithm>
+#include <type_traits>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -44,7 +46,13 @@ constexpr int MK_THREADS = 352;
 #else
 constexpr int MK_THREADS = 320;
 #endif
-constexpr int MK_NST = 5;
+#ifndef MK_NST_N
+#define MK_NST_N 5
+#endif
+#ifndef MK_OCC
+#define MK_OCC 1  // experiment build: -DMK_OCC=2 -DMK_NST_N=2 lets two instances (two half-batch lanes) share every SM
+#endif
+constexpr int MK_NST = MK_NST_N;
 constexpr int MK_STAGE = 40960;
 constexpr int MK_WTILE = 32768;  // one (tile, k-block): [hi 128x64 bf16 swizzled][lo ...]
 constexpr int MK_XOFF = 32768;   // activation tile inside a stage: hi [32][64] bf16 (4 KB) then lo (4 KB)
@@ -62,6 +70,16 @@ constexpr int MK_CROSS_VR = 208;  // keys per cross-V chunk (kv24: 192 bytes per
 #define MK_STAMP(ptr, i) do { if (ptr) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); (ptr)[i] = _t; } } while (0)
 #else
 #define MK_STAMP(ptr, i) do { } while (0)
+#endif
+
+// cycle accounting of the cross-attention phase, profiling build only (MG_B200_CFLAGS=-DMK_XPROF, MG_MEGA_PROF=<file>,
+// reader: tools/cross_phase_cycles.py): per CTA, layer NL/2 of the last step -- producer: cycles waiting for a free
+// stage / issuing; consumers (thread 0): cycles waiting for data / in the arithmetic / in the barrier + release, and the
+// per-item sections outside the chunk loops (head: query + mask loads, softmax, tail: output reduction)
+#ifdef MK_XPROF
+#define MK_XP(...) __VA_ARGS__
+#else
+#define MK_XP(...)
 #endif
 
 // CTA-local progress flags (producer -> consumers "loads issued" counter, consumers -> producer phase counter) are
@@ -189,7 +207,7 @@ constexpr int MK_SMEM = MK_OFF_TAB + MK_MAX_LAYERS * (int)sizeof(MegaLayer) + 10
 static_assert(sizeof(MegaLayer) % 8 == 0 && MK_OFF_TAB % 8 == 0, "layer table is copied in 8-byte words");
 static_assert(MK_SMEM <= 227 * 1024, "shared memory budget");
 
-__global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid_constant__ MegaParams p) {
+__global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const __grid_constant__ MegaParams p) {
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic (not an integer round trip) keeps the shared address space: LDS/STS instead of generic LD/ST
   uint8_t* const ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -247,9 +265,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
   const int self_nblk = (step + 31) >> 5;
   const int self_nkc = (self_nblk + MK_SELF_KB - 1) / MK_SELF_KB;
   const int self_nvc = (step + MK_SELF_VR - 1) / MK_SELF_VR;
-  const int cross_rk = min(64, (MK_STAGE / (Mp * 3)) & ~1);  // d-rows per K chunk, even (16-byte sized copies)
+  int cross_rk = min(64, (MK_STAGE / (Mp * 3)) & ~1);  // d-rows per K chunk, even (16-byte sized copies)
+  int cross_vr = MK_CROSS_VR;
+  // experiment switches (MG_MEGA_CROSS_RK / MG_MEGA_CROSS_VR): smaller chunks = emptier ring stages
+  if (p.cross_rk > 0) cross_rk = max(2, min(cross_rk, p.cross_rk & ~1));
+  if (p.cross_vr > 0) cross_vr = max(16, min(cross_vr, p.cross_vr & ~7));
   const int cross_nkc = (64 + cross_rk - 1) / cross_rk;
-  const int cross_nvc = (Mp + MK_CROSS_VR - 1) / MK_CROSS_VR;
+  const int cross_nvc = (Mp + cross_vr - 1) / cross_vr;
   // attention items are spread over Ga <= G CTAs so that every one of them gets the same count (512 items over 148
   // CTAs would be 3 or 4 each and the phase would run at the pace of 4; over 128 CTAs it is exactly 4 each and HBM,
   // not the SM count, stays the limit)
@@ -288,7 +310,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
     if (lane == 0) {
       RingPos r;
       int n_put = 0;
-      const int max_inflight = p.max_inflight;
+      const int max_inflight = min(p.max_inflight, MK_NST);
       // everything streamed through the ring is read exactly once per step: evict-first keeps the small hot data
       // (activations, masks, norm weights, bias tables) resident in L2 underneath a ~9 GB/step stream
       uint64_t pol_stream;
@@ -338,10 +360,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
           if (++spins > (1u << 26)) mk_die(1, bar, parity);
         }
       };
+      MK_XP(long long xp_wait = 0; long long xp_issue = 0; long long xp_n = 0;)
       for (int l = 0; l <= NL; ++l) {
         const MegaLayer& L = s_layers[min(l, NL - 1)];
         const int nph = l < NL ? MK_NPH : 1;
         for (int ph = 0; ph < nph; ++ph) {
+          MK_XP(if (p.prof && l == NL / 2 && ph == MK_PH_CROSS + 1) {
+            unsigned long long* q = p.prof + ((size_t)g * 512 + 440) * 2;
+            q[0] = xp_wait; q[1] = xp_issue; q[2] = xp_n;
+          })
           const bool attn = l < NL && (ph == MK_PH_SELF || ph == MK_PH_CROSS);
           if (pf_total) {
             if (l < NL && ph == MK_PH_CROSS) { pf_cur = 0; pf_on = false; }
@@ -375,7 +402,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               // kv24 block per (image, head): [K hi 2n][K lo n][V hi 2n][V lo n], n = 64 * Mp; tot / chunk count the
               // 16-bit plane, every chunk is followed in its stage by the matching half-sized piece of the 8-bit plane
               base0 = L.ckv; sa0 = (size_t)Mp * 384; tot0 = (uint32_t)Mp * 128u; chunk0 = (uint32_t)cross_rk * Mp * 2u;
-              base1 = L.ckv + (size_t)Mp * 192; sa1 = sa0; tot1 = tot0; chunk1 = MK_CROSS_VR * 128;
+              base1 = L.ckv + (size_t)Mp * 192; sa1 = sa0; tot1 = tot0; chunk1 = (uint32_t)cross_vr * 128u;
               lo_off = (uint32_t)Mp * 128u;
             }
           } else {
@@ -406,12 +433,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                   const int major = it / div, minor = it - major * div;
                   const uint8_t* const src0 = sidx ? base1 + major * sa1 : base0 + major * sa0 + minor * sb0;
                   // cap the loads this SM keeps in flight (a deeper queue adds latency, not bandwidth)
+                  MK_XP(const long long xt0 = clock64();)
                   if (n_put >= max_inflight) {
                     const int m = n_put - max_inflight;
                     mk_wait(bar_full + 8 * (m % MK_NST), (uint32_t)((m / MK_NST) & 1));
                   }
                   ++n_put;
                   wait_slot(bar_empty + 8 * r.s, r.ph ^ 1);
+                  MK_XP(const long long xt1 = clock64();)
                   const uint32_t fb = bar_full + 8 * r.s;
                   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(lo_off ? bytes + (bytes >> 1) : bytes) : "memory");
                   asm volatile(
@@ -428,6 +457,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                   r.adv();
                   __threadfence_block();
                   MK_FLAG_ST(s_issued, n_put);
+                  MK_XP(if (is_cross && l == NL / 2) { xp_wait += xt1 - xt0; xp_issue += clock64() - xt1; ++xp_n; })
                 }
               }
             }
@@ -719,13 +749,16 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
         } else if (l < NL && ph == MK_PH_CROSS) {
           // ---------------------------------------------------------------------------------- cross-attention
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
-          // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = pair of adjacent keys.
+          // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = quad of adjacent keys.
           const unsigned x_epoch = (unsigned)(step * NL + l + 1);  // unique per (step, layer): the flags need no reset
           int rs_b = -1;    // image whose row scale rsb holds: consecutive entries are mostly heads of one image
           float rsb = 0.f;
+          MK_XP(long long xc_wait = 0, xc_math = 0, xc_sync = 0, xc_head = 0, xc_soft = 0, xc_tail = 0, xc_n = 0;
+                const long long xc_begin = clock64(); long long xc_t = xc_begin;)
           for (int e = 0; e < x_entries; ++e) {
             int it, passes;
             cross_entry(e, it, passes);
+            MK_XP(xc_t = clock64();)
             const int b = it / H, h = it - b * H;
             float* const xp = p.xp + (size_t)it * (Mp + 4);  // published probabilities of a split item
             float sum;
@@ -741,34 +774,64 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               if (new_b && 4 * ct < D) xr = ldcg4(xin + (int64_t)b * D + 4 * ct);
               int mk8[8];  // this thread's mask bits, fetched now so their latency hides under the K pass
 #pragma unroll
-              for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(2 * (ct + 256 * (i >> 1)) + (i & 1), Mp - 1)];
+              for (int i = 0; i < 8; ++i) mk8[i] = p.mem_mask[(int64_t)b * Mp + min(4 * ct + (i & 3) + 1024 * (i >> 2), Mp - 1)];
+              const bool kq0 = 128 * cw < Mp, kq1 = 1024 + 128 * cw < Mp;  // this warp's two key quads-of-32 exist (warp-uniform)
               cons_sync();
               float acc[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+              MK_XP(xc_head += clock64() - xc_t;)
               for (int c = 0; c < cross_nkc; ++c) {
+                MK_XP(const long long w0 = clock64();)
                 mk_wait(bar_full + 8 * r.s, r.ph);
+                MK_XP(const long long w1 = clock64(); xc_wait += w1 - w0; ++xc_n;)
                 const uint8_t* buf = ring + (size_t)r.s * MK_STAGE;
                 const int r0 = c * cross_rk, rows = min(cross_rk, 64 - r0);
-                const uint32_t* hrow = reinterpret_cast<const uint32_t*>(buf) + ct;
-                const uint16_t* lrow = reinterpret_cast<const uint16_t*>(buf + (size_t)rows * Mp * 2) + ct;
+                const int rows_math = (p.dbg & 8) ? 0 : rows;  // MG_MEGA_DBG bit 3: stream only, no K-pass arithmetic (wrong ids; timing A/B)
+                // thread = 4 adjacent keys (+ the 4 keys 1024 further on): one 8-byte load of the 16-bit plane and one
+                // 4-byte load of the 8-bit plane per quad -- the pass is bound by shared-memory wavefronts (the bulk
+                // copies' writes included), and this layout needs 3 per 128 keys and d-row where key PAIRS with 2-byte
+                // loads of the 8-bit plane needed 4 and ran every warp over all 2048 key slots.  Warps whose keys lie
+                // beyond Mp skip the loads (warp-uniform); threads past the row's end inside an active warp read the
+                // next row / plane (inside this CTA's shared memory), their sums are never used.
+                const uint2* hrow = reinterpret_cast<const uint2*>(buf) + ct;
+                const uint32_t* lrow = reinterpret_cast<const uint32_t*>(buf + (size_t)rows * Mp * 2) + ct;
+                const int pitch = Mp >> 2;
+                // (the loop exists once per warp-uniform case so that its body is branch-free: loads first, then arithmetic)
+                auto k_rows = [&](auto both) {
 #pragma unroll 2
-                for (int rr = 0; rr < rows; ++rr) {
-                  const float qd = s_q[r0 + rr];
-                  // pairs >= Mp/2 read past the row (still inside this CTA's shared memory); their sums are never used
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const uint32_t h2 = hrow[256 * i], l2 = lrow[256 * i];
-                    acc[2 * i] += qd * __uint_as_float(__byte_perm(h2, l2, 0x1046));
-                    acc[2 * i + 1] += qd * __uint_as_float(__byte_perm(h2, l2, 0x3256));
+                  for (int rr = 0; rr < rows_math; ++rr) {
+                    const float qd = s_q[r0 + rr];
+                    const uint2 h0 = hrow[0];
+                    const uint32_t l0 = lrow[0];
+                    uint2 h1 = make_uint2(0u, 0u);
+                    uint32_t l1 = 0u;
+                    if constexpr (decltype(both)::value) { h1 = hrow[256]; l1 = lrow[256]; }
+                    hrow += pitch;
+                    lrow += pitch;
+                    const uint32_t la = __byte_perm(l0, 0u, 0x4240), lb = __byte_perm(l0, 0u, 0x4341);
+                    acc[0] += qd * __uint_as_float(__byte_perm(h0.x, la, 0x1045));
+                    acc[1] += qd * __uint_as_float(__byte_perm(h0.x, lb, 0x3245));
+                    acc[2] += qd * __uint_as_float(__byte_perm(h0.y, la, 0x1065));
+                    acc[3] += qd * __uint_as_float(__byte_perm(h0.y, lb, 0x3265));
+                    if constexpr (decltype(both)::value) {
+                      const uint32_t lc = __byte_perm(l1, 0u, 0x4240), ld = __byte_perm(l1, 0u, 0x4341);
+                      acc[4] += qd * __uint_as_float(__byte_perm(h1.x, lc, 0x1045));
+                      acc[5] += qd * __uint_as_float(__byte_perm(h1.x, ld, 0x3245));
+                      acc[6] += qd * __uint_as_float(__byte_perm(h1.y, lc, 0x1065));
+                      acc[7] += qd * __uint_as_float(__byte_perm(h1.y, ld, 0x3265));
+                    }
                   }
-                  hrow += Mp >> 1;
-                  lrow += Mp >> 1;
-                }
+                };
+                if (kq1) k_rows(std::true_type{});
+                else if (kq0) k_rows(std::false_type{});
+                MK_XP(const long long w2 = clock64(); xc_math += w2 - w1;)
                 cons_sync();
                 if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
                 r.adv();
+                MK_XP(xc_sync += clock64() - w2;)
               }
+              MK_XP(xc_t = clock64();)
               if (new_b) {
                 rsb = rsqrtf(mk_block_reduce((xr.x * xr.x + xr.y * xr.y) + (xr.z * xr.z + xr.w * xr.w), s_b, cw, lane, 0) / (float)D + p.eps);
                 rs_b = b;
@@ -776,7 +839,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               float mx = -INFINITY;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
+                const int m = 4 * ct + (i & 3) + 1024 * (i >> 2);
                 const bool ok = m < Mp;
                 acc[i] = ok ? acc[i] * rsb + (mk8[i] ? 0.f : -3.4028234663852886e38f) : -INFINITY;
                 mx = fmaxf(mx, acc[i]);
@@ -785,7 +848,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               sum = 0.f;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int m = 2 * (ct + 256 * (i >> 1)) + (i & 1);
+                const int m = 4 * ct + (i & 3) + 1024 * (i >> 2);
                 if (m < Mp) {
                   const float ev = expf(acc[i] - mx);
                   s_sc[m] = ev;
@@ -820,13 +883,16 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
             }
             // ---- V pass
             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            MK_XP(xc_soft += clock64() - xc_t;)
             for (int c = 0; c < cross_nvc; ++c) {
+              MK_XP(const long long w0 = clock64();)
               mk_wait(bar_full + 8 * r.s, r.ph);
+              MK_XP(const long long w1 = clock64(); xc_wait += w1 - w0; ++xc_n;)
               const uint8_t* buf = ring + (size_t)r.s * MK_STAGE;
-              const int m0 = c * MK_CROSS_VR, rows = min(MK_CROSS_VR, Mp - m0);
+              const int m0 = c * cross_vr, rows = min(cross_vr, Mp - m0);
               const uint8_t* lo_base = buf + (size_t)rows * 128;
 #pragma unroll 2
-              for (int jj = r16; jj < rows; jj += 16) {
+              for (int jj = (p.dbg & 16) ? rows : r16; jj < rows; jj += 16) {  // MG_MEGA_DBG bit 4: stream only, no V-pass arithmetic
                 const uint2 h4 = *reinterpret_cast<const uint2*>(buf + ((size_t)jj * 64 + 4 * c16) * 2);
                 const uint32_t l4 = *reinterpret_cast<const uint32_t*>(lo_base + (size_t)jj * 64 + 4 * c16);
                 const float pj = s_sc[m0 + jj];
@@ -835,10 +901,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
                 a4.z += pj * __uint_as_float((h4.y << 16) | ((l4 >> 8) & 0xff00u));
                 a4.w += pj * __uint_as_float((h4.y & 0xffff0000u) | ((l4 >> 16) & 0xff00u));
               }
+              MK_XP(const long long w2 = clock64(); xc_math += w2 - w1;)
               cons_sync();
               if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
               r.adv();
+              MK_XP(xc_sync += clock64() - w2;)
             }
+            MK_XP(xc_t = clock64();)
             reinterpret_cast<float4*>(s_red)[r16 * 16 + c16] = a4;
             cons_sync();
             if (ct < 64) {
@@ -848,7 +917,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_step_kernel(const __grid
               p.ctx[(int64_t)b * D + h * 64 + ct] = o / sum;
             }
             cons_sync();
+            MK_XP(xc_tail += clock64() - xc_t;)
           }
+          MK_XP(if (p.prof && ct == 0 && l == NL / 2) {
+            unsigned long long* q = p.prof + ((size_t)g * 512 + 448) * 2;
+            q[0] = xc_wait; q[1] = xc_math; q[2] = xc_sync; q[3] = xc_head; q[4] = xc_soft; q[5] = xc_tail; q[6] = xc_n;
+            q[7] = clock64() - xc_begin;
+          })
         } else {
           // ---------------------------------------------------------------------------------- linear
           // out[b][n] (+)= sum_k pro(x)[b][k] * W[n][k];  pro: 0 none, 1 RMSNorm weight (x*lnw staged; the row scale
@@ -1313,6 +1388,8 @@ int mega_max_ctas() {
     MG_CHECK_CUDA(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MK_SMEM));
     MG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel, MK_THREADS, MK_SMEM));
     n = (coop && per_sm >= 1) ? sms : 0;
+    // experiment switch (tools/ab_two_lanes.py): run the step on fewer CTAs
+    if (n > 0 && getenv("MG_MEGA_CTAS")) n = std::max(8, std::min(n, atoi(getenv("MG_MEGA_CTAS"))));
   }
   return n;
 }
@@ -1330,7 +1407,10 @@ void launch_decode_step(cudaStream_t st, const MegaParams& p, int n_ctas) {
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // MG_MEGA_NOCOOP=1 (experiments with two concurrent instances): plain launch; co-residency then rests on
+  // 1 CTA per SM and instances that together fill at most the chip
+  static const bool nocoop = getenv("MG_MEGA_NOCOOP") && getenv("MG_MEGA_NOCOOP")[0] == '1';
+  cfg.numAttrs = nocoop ? 0 : 1;
   MG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_step_kernel, p));
 }
 

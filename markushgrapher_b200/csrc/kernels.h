@@ -186,8 +186,9 @@ struct MegaParams {
   unsigned* bar_ctr;  // [2], zero before the first step
   int gate = 0;          // 1: attention K/V streams wait until the consumers enter their phase (measured: no gain)
   int* dbg_host = nullptr;  // host-mapped pinned words for the watchdog's diagnostics (may be null)
-  int dbg = 0;           // profiling builds (-DMK_FINE) only: 1 = skip the reductions, 2 = skip the TMEM loads
+  int dbg = 0;           // -DMK_FINE builds: 1 = skip the reductions, 2 = skip the TMEM loads; any build: 4 = evict-normal stream, 8 / 16 = no cross K / V arithmetic (stream only)
   int max_inflight = 5;  // bulk loads one SM keeps in flight (<= ring stages)
+  int cross_rk = 0, cross_vr = 0;  // experiments: d-rows per cross-K chunk / keys per cross-V chunk (0 = as many as fit a stage)
   // decode_mega.cu, producer: paced L2 prefetch of the first bytes of the coming cross-attention phase (0 = off)
   int l2pf = 384 * 1024;   // bytes per CTA and layer
   int l2pf_piece = 4096;   // bytes per prefetch instruction (multiple of 16)

@@ -3,6 +3,7 @@
 //   * the fork's Markushgrapher encoder forward (Swin branch + projector + UdopStack encoder + fusion concat;
 //     stock restatement transformers/models/udop/modeling_udop.py:1064-1256, models/swin/modeling_swin.py:534-913),
 //   * GenerationMixin.generate / _sample (transformers/generation/utils.py:2131, 2658-2842) for greedy decode.
+#include <cuda.h>  // types of the green-context driver API (entry points come from cudaGetDriverEntryPoint: no libcuda link)
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
@@ -81,6 +82,12 @@ struct Arena {
     Chunk c;
     c.cap = std::max(bytes, chunk_bytes);
     MG_CHECK_CUDA(cudaMalloc((void**)&c.base, c.cap));
+    // a chunk starts out zeroed (once, at allocation): padding rows / columns that no kernel writes then hold the same
+    // bytes whether the pages are fresh from the driver or recycled from an earlier allocation of this process
+    // (MG_ARENA_NOZERO: off for compute-sanitizer initcheck runs; MG_ARENA_POISON: 0xFF = NaN patterns instead, to
+    // flush out kernels whose results depend on bytes nobody wrote)
+    if (getenv("MG_ARENA_POISON")) MG_CHECK_CUDA(cudaMemset(c.base, 0xff, c.cap));
+    else if (!getenv("MG_ARENA_NOZERO")) MG_CHECK_CUDA(cudaMemset(c.base, 0, c.cap));
     c.used = bytes;
     total += c.cap;
     chunks.push_back(c);
@@ -231,6 +238,16 @@ struct mg_model {
       if (hs.ready) cudaEventDestroy(hs.ready);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (auto& a : ahead) {
+      a.persist.release();
+      a.scratch.release();
+      if (a.done) cudaEventDestroy(a.done);
+      if (a.begin) cudaEventDestroy(a.begin);
+    }
+    if (part.order) cudaEventDestroy(part.order);
+    if (part.s_small) cudaStreamDestroy(part.s_small);
+    if (part.s_big) cudaStreamDestroy(part.s_big);
+    // (the two green contexts live until the primary context goes away)
     if (own_stream) cudaStreamDestroy(own_stream);
     if (aux_stream) cudaStreamDestroy(aux_stream);
     for (auto& e : lane_ev)
@@ -337,6 +354,8 @@ struct mg_model {
   // copies one batch of host inputs into slot `s` on stream `cs` (max_length sizes the ids-out buffer)
   void stage_inputs(HostStage& s, cudaStream_t cs, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
                     const int64_t* mask, int out_cols) {
+    for (auto& a : ahead)  // a run-ahead encoding computed from this slot's previous contents is stale now
+      if (a.valid && s.buf && a.k_ids == s.d_ids && a.k_px == s.d_px) a.valid = false;
     const size_t n_ids = (size_t)B * Lt, n_px = (size_t)B * 3 * cfg.image_size * cfg.image_size;
     const size_t need = rup(n_ids * 8, 256) * 2 + rup(n_ids * 16, 256) + rup(n_px * 4, 256) + rup((size_t)B * out_cols * 8, 256);
     if (need > s.cap) {
@@ -363,6 +382,53 @@ struct mg_model {
     s.valid = true;
     s.seq = ++stage_seq;
   }
+
+  // ---- encoder run-ahead (mg_encode_ahead): while batch i decodes -- an HBM-bound loop that leaves the tensor cores
+  // idle -- the encoder of batch i+1 runs on a small SM partition of its own (CUDA green contexts); the decode loop
+  // then runs on the remaining SMs.  An EncSlot is one encoded batch together with the arenas it lives in; taking a
+  // slot swaps it with the model's current view (cur_*, mem*, persist, scratch), so nothing is copied.
+  struct EncSlot {
+    Arena persist, scratch;
+    int B = 0, Lt = 0, S = 0, Sp = 0, M = 0, Mp = 0;
+    float* mem = nullptr;
+    Planes mem_pl;
+    int* mem_mask = nullptr;
+    const void *k_ids = nullptr, *k_box = nullptr, *k_px = nullptr, *k_mask = nullptr;  // inputs it was computed from
+    bool valid = false;   // holds an encoded batch that no generate call has consumed yet
+    uint64_t seq = 0;
+    cudaEvent_t begin = nullptr, done = nullptr;  // on the small partition's stream
+    int64_t n_launch = 0;
+  };
+  EncSlot ahead[2];
+  float last_ahead_ms = 0.f;  // encoder time of the batch the last generate call took from a slot (on the small partition)
+  uint64_t ahead_seq = 0;
+  struct Partitions {
+    bool tried = false, ok = false;
+    CUgreenCtx g_small = nullptr, g_big = nullptr;
+    cudaStream_t s_small = nullptr, s_big = nullptr;
+    int n_small = 0, n_big = 0;
+    cudaEvent_t order = nullptr;
+  } part;
+  int run_ctas = 0;  // CTAs the fused decode step may use in the current generate call (0 = all SMs)
+  void swap_view(EncSlot& s) {
+    std::swap(persist, s.persist); std::swap(scratch, s.scratch);
+    std::swap(cur_B, s.B); std::swap(cur_Lt, s.Lt); std::swap(cur_S, s.S); std::swap(cur_Sp, s.Sp);
+    std::swap(cur_M, s.M); std::swap(cur_Mp, s.Mp);
+    std::swap(mem, s.mem); std::swap(mem_pl, s.mem_pl); std::swap(mem_mask, s.mem_mask);
+  }
+  bool ensure_partitions();
+  int find_ahead(int B, int Lt, const void* ids, const void* box, const void* px, const void* mask) const {
+    int best = -1;  // the OLDEST match: a caller that reuses its tensors has the next batch armed under the same keys
+    for (int i = 0; i < 2; ++i) {
+      const EncSlot& s = ahead[i];
+      if (s.valid && s.k_ids == ids && s.k_box == box && s.k_px == px && s.k_mask == mask && s.B == B && s.Lt == Lt &&
+          (best < 0 || s.seq < ahead[best].seq))
+        best = i;
+    }
+    return best;
+  }
+  void encode_ahead(cudaStream_t after, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
+                    const int64_t* amask);
 
   int64_t* ids_buf = nullptr;
   int64_t ids_cap = 0;
@@ -1141,6 +1207,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     if (getenv("MG_MEGA_DBG")) mp.dbg = atoi(getenv("MG_MEGA_DBG"));
     if (getenv("MG_MEGA_GATE")) mp.gate = atoi(getenv("MG_MEGA_GATE"));
     if (getenv("MG_MEGA_INFLIGHT")) mp.max_inflight = std::max(1, std::min(5, atoi(getenv("MG_MEGA_INFLIGHT"))));
+    if (getenv("MG_MEGA_CROSS_RK")) mp.cross_rk = atoi(getenv("MG_MEGA_CROSS_RK"));
+    if (getenv("MG_MEGA_CROSS_VR")) mp.cross_vr = atoi(getenv("MG_MEGA_CROSS_VR"));
     if (getenv("MG_MEGA_L2PF")) mp.l2pf = std::max(0, atoi(getenv("MG_MEGA_L2PF"))) * 1024;  // KB per CTA and layer
     if (getenv("MG_MEGA_L2PF_PIECE")) mp.l2pf_piece = std::max(0, atoi(getenv("MG_MEGA_L2PF_PIECE")) & ~15);
     if (getenv("MG_MEGA_L2PF_GAP")) mp.l2pf_gap = std::max(0, atoi(getenv("MG_MEGA_L2PF_GAP")));
@@ -1154,7 +1222,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     cudaStream_t ls = Ln.st;
     const int b0 = Ln.b0, bn = Ln.bn;
     if (use_mega) {
-      launch_decode_step(ls, mp, mega_ctas);
+      launch_decode_step(ls, mp, run_ctas > 0 ? std::min(mega_ctas, run_ctas) : mega_ctas);
       launch_greedy_select(ls, part_val, part_idx, n_part, logits, bn, V, Vld, shared, d, c.eos_token_id, c.pad_token_id,
                            ids_dev, max_length, finished, Ln.ctr, Ln.ctr + 1, Ln.ctr + 2, x,
                            step_logits, (int64_t)(max_length - 1) * V, V, forced, forced_ld, step_tok, step_ts,
@@ -1512,6 +1580,89 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
   catch (const mg::Error& e) { return mg::set_error(e); } \
   catch (const std::exception& e) { return mg::set_error(e); }
 
+// ================================================================================================= encoder run-ahead
+// Splits the SMs into a small group for the run-ahead encoder and the rest for the decode loop.  MG_AHEAD=0 switches the
+// feature off, MG_AHEAD_SMS sizes the small group (default 16: the fused decode step keeps 132 CTAs, and every linear
+// of the step has 128 work items, so only its cross-attention and LM-head phases lose SMs).
+bool mg_model::ensure_partitions() {
+  if (part.tried) return part.ok;
+  part.tried = true;
+  if (getenv("MG_AHEAD") && getenv("MG_AHEAD")[0] == '0') return false;
+  const int want = getenv("MG_AHEAD_SMS") ? std::max(8, atoi(getenv("MG_AHEAD_SMS"))) : 16;
+  auto entry = [](const char* name) -> void* {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return fn;
+  };
+  auto pDevGet = reinterpret_cast<CUresult (*)(CUdevice*, int)>(entry("cuDeviceGet"));
+  auto pGetRes = reinterpret_cast<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>(entry("cuDeviceGetDevResource"));
+  auto pSplit = reinterpret_cast<CUresult (*)(CUdevResource*, unsigned*, const CUdevResource*, CUdevResource*, unsigned, unsigned)>(
+      entry("cuDevSmResourceSplitByCount"));
+  auto pDesc = reinterpret_cast<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned)>(entry("cuDevResourceGenerateDesc"));
+  auto pCreate = reinterpret_cast<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned)>(entry("cuGreenCtxCreate"));
+  auto pStream = reinterpret_cast<CUresult (*)(CUstream*, CUgreenCtx, unsigned, int)>(entry("cuGreenCtxStreamCreate"));
+  if (!pDevGet || !pGetRes || !pSplit || !pDesc || !pCreate || !pStream) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  CUdevice cudev;
+  CUdevResource all, grp, rest;
+  unsigned n = 1;
+  CUdevResourceDesc d_small, d_big;
+  CUstream ss = nullptr, sb = nullptr;
+  if (pDevGet(&cudev, dev) != CUDA_SUCCESS || pGetRes(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  if ((int)all.sm.smCount < want + 64) return false;
+  if (pSplit(&grp, &n, &all, &rest, 0, (unsigned)want) != CUDA_SUCCESS || n < 1 || rest.sm.smCount < 64) return false;
+  if (pDesc(&d_small, &grp, 1) != CUDA_SUCCESS || pDesc(&d_big, &rest, 1) != CUDA_SUCCESS) return false;
+  if (pCreate(&part.g_small, d_small, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  if (pCreate(&part.g_big, d_big, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  if (pStream(&ss, part.g_small, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+  if (pStream(&sb, part.g_big, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return false;
+  part.s_small = reinterpret_cast<cudaStream_t>(ss);
+  part.s_big = reinterpret_cast<cudaStream_t>(sb);
+  part.n_small = (int)grp.sm.smCount;
+  part.n_big = (int)rest.sm.smCount;
+  if (cudaEventCreateWithFlags(&part.order, cudaEventDisableTiming) != cudaSuccess) return false;
+  part.ok = true;
+  return true;
+}
+
+// Runs the encoder of a batch on the small partition, ordered after everything queued on `after` (the inputs may
+// still be in flight there), into the free slot; returns once the work is queued.
+void mg_model::encode_ahead(cudaStream_t after, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
+                            const int64_t* amask) {
+  MG_REQUIRE(finalized, "mg_finalize has not been called");
+  MG_REQUIRE(part.ok, "encode_ahead without SM partitions");
+  int k = 0;  // a slot without a pending batch, else the older one (its batch is dropped: it was never asked for)
+  if (ahead[0].valid && (!ahead[1].valid || ahead[1].seq < ahead[0].seq)) k = 1;
+  EncSlot& S = ahead[k];
+  if (!S.done) {
+    MG_CHECK_CUDA(cudaEventCreate(&S.done));
+    MG_CHECK_CUDA(cudaEventCreate(&S.begin));
+  }
+  S.valid = false;
+  MG_CHECK_CUDA(cudaEventRecord(part.order, after));
+  MG_CHECK_CUDA(cudaStreamWaitEvent(part.s_small, part.order, 0));
+  MG_CHECK_CUDA(cudaEventRecord(S.begin, part.s_small));
+  const int64_t l0 = launches;
+  swap_view(S);
+  try {
+    encode(part.s_small, B, Lt, ids, bbox, px, amask);
+  } catch (...) {
+    swap_view(S);
+    throw;
+  }
+  swap_view(S);  // the slot now holds the encoded batch, the model its previous view
+  MG_CHECK_CUDA(cudaEventRecord(S.done, part.s_small));
+  S.k_ids = ids; S.k_box = bbox; S.k_px = px; S.k_mask = amask;
+  S.valid = true;
+  S.seq = ++ahead_seq;
+  S.n_launch = launches - l0;
+}
+
 extern "C" {
 
 int mg_device_available(void) {
@@ -1598,8 +1749,33 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
     st = m->own_stream;
   }
   const int64_t l0 = m->launches;
+  // a batch whose encoder ran ahead (mg_encode_ahead) is taken from its slot; while ANOTHER batch is being encoded ahead
+  // this call runs on the large SM partition, so that the two never compete for an SM
+  const int slot = m->find_ahead(B, Lt, input_ids, bbox, pixel_values, attn_mask);
+  bool other_pending = false;
+  for (int i = 0; i < 2; ++i) other_pending = other_pending || (i != slot && m->ahead[i].valid);
+  m->run_ctas = 0;
+  // NCCL collectives inside the decode loop (beam search across ranks, MG_DIST=nccl) stay on the caller's stream: let the
+  // run-ahead encoder finish first instead of partitioning
+  const bool nccl_in_loop = m->comm != nullptr && m->dist_all_ids != nullptr && (num_beams > 1 || !m->px_ok);
+  if (m->part.ok && other_pending && nccl_in_loop) MG_CHECK_CUDA(cudaStreamSynchronize(m->part.s_small));
+  if (m->part.ok && other_pending && !nccl_in_loop) {
+    MG_CHECK_CUDA(cudaEventRecord(m->part.order, st));
+    MG_CHECK_CUDA(cudaStreamWaitEvent(m->part.s_big, m->part.order, 0));
+    st = m->part.s_big;
+    m->run_ctas = m->part.n_big;
+  }
   MG_CHECK_CUDA(cudaEventRecord(m->ev[0], st));
-  m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
+  int took_slot = -1;
+  if (slot >= 0) {
+    mg_model::EncSlot& S = m->ahead[slot];
+    m->swap_view(S);
+    S.valid = false;
+    MG_CHECK_CUDA(cudaStreamWaitEvent(st, S.done, 0));
+    took_slot = slot;
+  } else {
+    m->encode(st, B, Lt, input_ids, bbox, pixel_values, attn_mask);
+  }
   MG_CHECK_CUDA(cudaEventRecord(m->ev[1], st));
   MG_CHECK_CUDA(cudaEventRecord(m->ev[3], st));
   MG_CHECK_CUDA(cudaEventRecord(m->ev[5], st));
@@ -1607,11 +1783,17 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
     m->generate(st, B, max_length, out_ids, out_len, step_logits, steps_run);
   else
     m->generate_beam(st, B, num_beams, max_length, out_ids, out_len, steps_run);
+  m->run_ctas = 0;
   MG_CHECK_CUDA(cudaEventRecord(m->ev[2], st));
-  MG_CHECK_CUDA(cudaEventSynchronize(m->ev[2]));
+  MG_CHECK_CUDA(cudaEventSynchronize(m->ev[2]));  // (also orders the caller's stream: the call is host-synchronous)
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_encode_ms, m->ev[0], m->ev[1]));
   MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_decode_ms, m->ev[1], m->ev[2]));
   m->last_launches = m->launches - l0;
+  m->last_ahead_ms = 0.f;
+  if (took_slot >= 0) {  // the encoder ran ahead on the small partition: its own duration and launches
+    MG_CHECK_CUDA(cudaEventElapsedTime(&m->last_ahead_ms, m->ahead[took_slot].begin, m->ahead[took_slot].done));
+    m->last_launches += m->ahead[took_slot].n_launch;
+  }
   MG_API_END
 }
 
@@ -1798,6 +1980,55 @@ int mg_prefetch_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const
   if (!m->copy_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   const int slot = m->pick_stage_slot();  // never a slot whose batch is still waiting for its generate call
   m->stage_inputs(m->stage[slot], m->copy_stream, B, Lt, input_ids, bbox, pixel_values, attn_mask, max_length);
+  MG_API_END
+}
+
+int mg_encode_ahead(mg_model* m, void* stream, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                    const float* pixel_values, const int64_t* attn_mask, int32_t* armed) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values, "null argument");
+  MG_REQUIRE(m->finalized, "mg_finalize has not been called");
+  MG_REQUIRE(B > 0 && Lt > 0, "empty batch");
+  if (armed) *armed = 0;
+  if (m->ensure_partitions()) {
+    m->encode_ahead(static_cast<cudaStream_t>(stream), B, Lt, input_ids, bbox, pixel_values, attn_mask);
+    if (armed) *armed = 1;
+  }
+  MG_API_END
+}
+
+int mg_encode_ahead_host(mg_model* m, int B, int Lt, const int64_t* input_ids, const float* bbox,
+                         const float* pixel_values, const int64_t* attn_mask, int max_length, int32_t* armed) {
+  MG_API_BEGIN
+  MG_REQUIRE(m && input_ids && bbox && pixel_values, "null argument");
+  MG_REQUIRE(m->finalized, "mg_finalize has not been called");
+  MG_REQUIRE(B > 0 && Lt > 0 && max_length >= 2, "bad sizes");
+  if (armed) *armed = 0;
+  if (!m->copy_stream) MG_CHECK_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  const int slot = m->pick_stage_slot();
+  mg_model::HostStage& S = m->stage[slot];
+  m->stage_inputs(S, m->copy_stream, B, Lt, input_ids, bbox, pixel_values, attn_mask, max_length);
+  if (m->ensure_partitions()) {
+    m->encode_ahead(m->copy_stream, B, Lt, S.d_ids, S.d_box, S.d_px, attn_mask ? S.d_mask : nullptr);
+    if (armed) *armed = 1;
+  }
+  MG_API_END
+}
+
+int mg_ahead_reset(mg_model* m) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (m->part.ok) MG_CHECK_CUDA(cudaStreamSynchronize(m->part.s_small));
+  for (auto& a : m->ahead) a.valid = false;
+  MG_API_END
+}
+
+int mg_last_ahead(mg_model* m, float* encoder_ms, int32_t* sms_encoder, int32_t* sms_decoder) {
+  MG_API_BEGIN
+  MG_REQUIRE(m, "null model");
+  if (encoder_ms) *encoder_ms = m->last_ahead_ms;
+  if (sms_encoder) *sms_encoder = m->part.ok ? m->part.n_small : 0;
+  if (sms_decoder) *sms_decoder = m->part.ok ? m->part.n_big : 0;
   MG_API_END
 }
 

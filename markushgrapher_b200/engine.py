@@ -192,6 +192,54 @@ class MGEngine:
                                              int(max_length))
         _lib.check(rc, "mg_prefetch_host")
 
+    # ------------------------------------------------------------------ encoder run-ahead (a stream of batches)
+    def encode_ahead(self, input_ids, bbox, pixel_values, attention_mask=None) -> bool:
+        """queue the encoder of the NEXT batch on its own small SM partition and return at once; the generate /
+        generate_dist call that later gets the very same device tensors (int64 / float32, contiguous, unchanged) takes
+        the finished encoder memory.  False if SM partitioning is unavailable (nothing queued)."""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, self.device)
+        self._ahead_keep = (getattr(self, "_ahead_keep", ()) + ((ids, box, px, am),))[-2:]  # the library reads them later
+        armed = ctypes.c_int32(0)
+        L = _lib.lib()
+        L.mg_encode_ahead.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5
+        with torch.cuda.device(self.device):
+            rc = L.mg_encode_ahead(self._h, _lib.cur_stream(), B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px),
+                                   _lib.ptr(am), ctypes.addressof(armed))
+        _lib.check(rc, "mg_encode_ahead")
+        return bool(armed.value)
+
+    def encode_ahead_host(self, input_ids, bbox, pixel_values, attention_mask=None, max_length=512) -> bool:
+        """prefetch_host + run-ahead encoder on the staged copy; consumed by the generate_host call that passes the
+        same pinned HOST tensors"""
+        ids, box, px, am, B, Lt = self._prep(input_ids, bbox, pixel_values, attention_mask, "cpu")
+        for t, o in ((ids, input_ids), (box, bbox), (px, pixel_values)):
+            if t.data_ptr() != o.data_ptr():
+                raise _lib.MgError("encode_ahead_host needs contiguous int64 / float32 host tensors (no conversion copy)")
+        armed = ctypes.c_int32(0)
+        L = _lib.lib()
+        L.mg_encode_ahead_host.argtypes = ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 +
+                                           [ctypes.c_int, ctypes.c_void_p])
+        with torch.cuda.device(self.device):
+            rc = L.mg_encode_ahead_host(self._h, B, Lt, _lib.ptr(ids), _lib.ptr(box), _lib.ptr(px), _lib.ptr(am),
+                                        int(max_length), ctypes.addressof(armed))
+        _lib.check(rc, "mg_encode_ahead_host")
+        return bool(armed.value)
+
+    def ahead_reset(self):
+        """end of a stream of batches: wait for a run-ahead encoder in flight, drop batches nobody asked for"""
+        L = _lib.lib()
+        L.mg_ahead_reset.argtypes = [ctypes.c_void_p]
+        with torch.cuda.device(self.device):
+            _lib.check(L.mg_ahead_reset(self._h), "mg_ahead_reset")
+
+    def last_ahead(self):
+        """(encoder ms on its partition for the batch the last generate call took from a slot, SMs encoder, SMs decoder)"""
+        ms, a, b = ctypes.c_float(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        L = _lib.lib()
+        L.mg_last_ahead.argtypes = [ctypes.c_void_p] * 4
+        _lib.check(L.mg_last_ahead(self._h, ctypes.addressof(ms), ctypes.addressof(a), ctypes.addressof(b)), "mg_last_ahead")
+        return {"encoder_ms": ms.value, "sms_encoder": a.value, "sms_decoder": b.value}
+
     # ------------------------------------------------------------------ multi-GPU (one process per GPU)
     def comm_init_from_torch(self, group=None):
         """join an NCCL communicator owned by the library; the 128-byte id travels over torch.distributed"""
