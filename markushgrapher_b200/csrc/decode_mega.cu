@@ -881,8 +881,12 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               sum = __ldcg(xp + Mp);
               cons_sync();
             }
-            // ---- V pass
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            // ---- V pass: thread = 8 adjacent d-columns of the keys  jj == ct / 8 (mod 32)  -- one 16-byte load of the
+            // 16-bit plane, one 8-byte load of the 8-bit plane and one probability per key row and thread
+            float av[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) av[i] = 0.f;
+            const int r32 = ct >> 3, c8 = ct & 7;
             MK_XP(xc_soft += clock64() - xc_t;)
             for (int c = 0; c < cross_nvc; ++c) {
               MK_XP(const long long w0 = clock64();)
@@ -890,16 +894,23 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               MK_XP(const long long w1 = clock64(); xc_wait += w1 - w0; ++xc_n;)
               const uint8_t* buf = ring + (size_t)r.s * MK_STAGE;
               const int m0 = c * cross_vr, rows = min(cross_vr, Mp - m0);
-              const uint8_t* lo_base = buf + (size_t)rows * 128;
+              const uint8_t* hp = buf + c8 * 16;
+              const uint8_t* lp = buf + (size_t)rows * 128 + c8 * 8;
 #pragma unroll 2
-              for (int jj = (p.dbg & 16) ? rows : r16; jj < rows; jj += 16) {  // MG_MEGA_DBG bit 4: stream only, no V-pass arithmetic
-                const uint2 h4 = *reinterpret_cast<const uint2*>(buf + ((size_t)jj * 64 + 4 * c16) * 2);
-                const uint32_t l4 = *reinterpret_cast<const uint32_t*>(lo_base + (size_t)jj * 64 + 4 * c16);
+              for (int jj = (p.dbg & 16) ? rows : r32; jj < rows; jj += 32) {  // MG_MEGA_DBG bit 4: stream only, no V-pass arithmetic
+                const uint4 hh = *reinterpret_cast<const uint4*>(hp + (size_t)jj * 128);
+                const uint2 ll = *reinterpret_cast<const uint2*>(lp + (size_t)jj * 64);
                 const float pj = s_sc[m0 + jj];
-                a4.x += pj * __uint_as_float((h4.x << 16) | ((l4 & 0xffu) << 8));
-                a4.y += pj * __uint_as_float((h4.x & 0xffff0000u) | (l4 & 0xff00u));
-                a4.z += pj * __uint_as_float((h4.y << 16) | ((l4 >> 8) & 0xff00u));
-                a4.w += pj * __uint_as_float((h4.y & 0xffff0000u) | ((l4 >> 16) & 0xff00u));
+                const uint32_t la = __byte_perm(ll.x, 0u, 0x4240), lb = __byte_perm(ll.x, 0u, 0x4341);
+                const uint32_t lc = __byte_perm(ll.y, 0u, 0x4240), ld = __byte_perm(ll.y, 0u, 0x4341);
+                av[0] += pj * __uint_as_float(__byte_perm(hh.x, la, 0x1045));
+                av[1] += pj * __uint_as_float(__byte_perm(hh.x, lb, 0x3245));
+                av[2] += pj * __uint_as_float(__byte_perm(hh.y, la, 0x1065));
+                av[3] += pj * __uint_as_float(__byte_perm(hh.y, lb, 0x3265));
+                av[4] += pj * __uint_as_float(__byte_perm(hh.z, lc, 0x1045));
+                av[5] += pj * __uint_as_float(__byte_perm(hh.z, ld, 0x3245));
+                av[6] += pj * __uint_as_float(__byte_perm(hh.w, lc, 0x1065));
+                av[7] += pj * __uint_as_float(__byte_perm(hh.w, ld, 0x3265));
               }
               MK_XP(const long long w2 = clock64(); xc_math += w2 - w1;)
               cons_sync();
@@ -908,12 +919,22 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               MK_XP(xc_sync += clock64() - w2;)
             }
             MK_XP(xc_t = clock64();)
-            reinterpret_cast<float4*>(s_red)[r16 * 16 + c16] = a4;
+            // the four key residues of a warp through shuffles, the eight warps through shared memory
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              av[i] += __shfl_xor_sync(0xffffffffu, av[i], 8);
+              av[i] += __shfl_xor_sync(0xffffffffu, av[i], 16);
+            }
+            if (lane < 8) {
+              float4* dst = reinterpret_cast<float4*>(s_red + cw * 64 + lane * 8);
+              dst[0] = make_float4(av[0], av[1], av[2], av[3]);
+              dst[1] = make_float4(av[4], av[5], av[6], av[7]);
+            }
             cons_sync();
             if (ct < 64) {
               float o = 0.f;
-#pragma unroll 4
-              for (int rr = 0; rr < 16; ++rr) o += s_red[rr * 64 + ct];
+#pragma unroll
+              for (int w = 0; w < 8; ++w) o += s_red[w * 64 + ct];
               p.ctx[(int64_t)b * D + h * 64 + ct] = o / sum;
             }
             cons_sync();
