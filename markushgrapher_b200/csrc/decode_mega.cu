@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
             MK_XP(xc_t = clock64();)
             const int b = it / H, h = it - b * H;
             float* const xp = p.xp + (size_t)it * (Mp + 4);  // published probabilities of a split item
-            float sum;
+            float* const s_r2 = s_part + (e & 1) * 32;       // [0, 16) reduction pairs, [16, 24) partial sums; alternates per entry
             if (passes & 1) {
               // ---- K pass: scores of this thread's key pairs, mask, softmax numerators into s_sc
               // q is the UNSCALED cross query (accumulated by phases 0 and 2); its RMSNorm row scale
@@ -832,34 +832,57 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                 MK_XP(xc_sync += clock64() - w2;)
               }
               MK_XP(xc_t = clock64();)
-              if (new_b) {
-                rsb = rsqrtf(mk_block_reduce((xr.x * xr.x + xr.y * xr.y) + (xr.z * xr.z + xr.w * xr.w), s_b, cw, lane, 0) / (float)D + p.eps);
-                rs_b = b;
-              }
-              float mx = -INFINITY;
+              // ONE reduction round for both block-wide values: the sum of squares of the residual row (new image only)
+              // and the largest unmasked raw score.  rsb > 0 and rounding is monotonic, so max_i fl(acc_i * rsb) =
+              // fl(max_i acc_i * rsb); a masked key's value acc * rsb + finfo.min is exactly finfo.min.  The softmax
+              // denominator is only needed after the V pass: the warps' partial sums wait in shared memory until then.
+              float ssq = (xr.x * xr.x + xr.y * xr.y) + (xr.z * xr.z + xr.w * xr.w);
+              float mraw = -INFINITY;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int m = 4 * ct + (i & 3) + 1024 * (i >> 2);
-                const bool ok = m < Mp;
-                acc[i] = ok ? acc[i] * rsb + (mk8[i] ? 0.f : -3.4028234663852886e38f) : -INFINITY;
-                mx = fmaxf(mx, acc[i]);
+                if (m < Mp && mk8[i]) mraw = fmaxf(mraw, acc[i]);
               }
-              mx = mk_block_reduce(mx, s_b, cw, lane, 1);
-              sum = 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+                mraw = fmaxf(mraw, __shfl_xor_sync(0xffffffffu, mraw, o));
+              }
+              if (lane == 0) { s_r2[cw] = ssq; s_r2[8 + cw] = mraw; }
+              cons_sync();
+              if (new_b) {
+                float t = s_r2[0];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) t += s_r2[w];
+                rsb = rsqrtf(t / (float)D + p.eps);
+                rs_b = b;
+              }
+              float mx = s_r2[8];
+#pragma unroll
+              for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_r2[8 + w]);
+              // every key masked: all values equal finfo.min (uniform attention, like the reference's additive mask)
+              mx = (mx == -INFINITY) ? -3.4028234663852886e38f : mx * rsb;
+              float psum = 0.f;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int m = 4 * ct + (i & 3) + 1024 * (i >> 2);
                 if (m < Mp) {
-                  const float ev = expf(acc[i] - mx);
+                  const float ev = expf((acc[i] * rsb + (mk8[i] ? 0.f : -3.4028234663852886e38f)) - mx);
                   s_sc[m] = ev;
                   if (passes == 1) xp[m] = ev;  // the V pass of this item runs on the next CTA
-                  sum += ev;
+                  psum += ev;
                 }
               }
-              sum = mk_block_reduce(sum, s_b, cw, lane, 0);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+              if (lane == 0) s_r2[16 + cw] = psum;
+              cons_sync();  // probabilities and the warps' partial sums visible
               if (passes == 1) {
                 if (ct == 0) {
-                  xp[Mp] = sum;
+                  float t = s_r2[16];
+#pragma unroll
+                  for (int w = 1; w < 8; ++w) t += s_r2[16 + w];
+                  xp[Mp] = t;
                   __threadfence();  // cumulative: the other threads' stores were ordered before it by the barrier above
                   atomicExch(p.xflag + it, x_epoch);
                 }
@@ -878,7 +901,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               }
               cons_sync();
               for (int m = ct; m < Mp; m += 256) s_sc[m] = __ldcg(xp + m);
-              sum = __ldcg(xp + Mp);
+              if (ct < 8) s_r2[16 + ct] = ct == 0 ? __ldcg(xp + Mp) : 0.f;
               cons_sync();
             }
             // ---- V pass: thread = 8 adjacent d-columns of the keys  jj == ct / 8 (mod 32)  -- one 16-byte load of the
@@ -935,9 +958,13 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               float o = 0.f;
 #pragma unroll
               for (int w = 0; w < 8; ++w) o += s_red[w * 64 + ct];
-              p.ctx[(int64_t)b * D + h * 64 + ct] = o / sum;
+              float t = s_r2[16];
+#pragma unroll
+              for (int w = 1; w < 8; ++w) t += s_r2[16 + w];
+              p.ctx[(int64_t)b * D + h * 64 + ct] = o / t;
             }
-            cons_sync();
+            // no trailing barrier: s_red is next written after the next entry's V pass (barriers in between), s_q and
+            // s_sc after its first barrier, and the reduction scratch alternates per entry
             MK_XP(xc_tail += clock64() - xc_t;)
           }
           MK_XP(if (p.prof && ct == 0 && l == NL / 2) {
