@@ -49,6 +49,11 @@ constexpr int MK_THREADS = 320;
 #ifndef MK_NST_N
 #define MK_NST_N 5
 #endif
+#ifndef MK_XUNROLL
+#define MK_XUNROLL 2  // d-rows (K pass) / key rows (V pass) of the cross-attention inner loops in flight per thread
+#endif
+#define MK_PRAGMA_(x) _Pragma(#x)
+#define MK_PRAGMA(x) MK_PRAGMA_(x)
 #ifndef MK_OCC
 #define MK_OCC 1  // experiment build: -DMK_OCC=2 -DMK_NST_N=2 lets two instances (two half-batch lanes) share every SM
 #endif
@@ -608,6 +613,8 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
           float* const red_g = q_g + 128;
           const int nch = self_nkc + self_nvc;
           auto gsync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(4 + gi) : "memory"); };
+          MK_XP(long long xs_wait = 0, xs_kmath = 0, xs_vmath = 0, xs_head = 0, xs_soft = 0, xs_tail = 0, xs_sync = 0;
+                const long long xs_begin = clock64(); long long xs_t = xs_begin;)
           for (int k0 = 0; k0 < my_attn; k0 += MK_SELF_NG) {
             const int ng = min(MK_SELF_NG, my_attn - k0);
             if (gi < ng) {
@@ -630,6 +637,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                 bias8[i] = j <= step ? p.dec_bias[p.lut[step - j] * H + h] : 0.f;
               }
               gsync();
+              MK_XP(xs_head += clock64() - xs_t;)
               // scores over the cached keys stay in registers: the thread that scores key j also owns it below
               float s8[8];
 #pragma unroll
@@ -644,6 +652,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                   // group's) may still be in flight, and a parity wait two phases ahead would alias.  The producer
                   // issues a load only after the stage's previous occupant has landed and been consumed, so first
                   // wait until this load has been issued, then for it to land.
+                  MK_XP(const long long w0 = clock64();)
                   {
                     const int seq = r.n + c * ng + gi;
                     uint32_t spins = 0;
@@ -651,6 +660,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                       if (++spins > (1u << 26)) mk_die(4, (uint32_t)seq, (uint32_t)*s_issued);
                   }
                   mk_wait(bar_full + 8 * st, par);
+                  MK_XP(const long long w1 = clock64(); xs_wait += w1 - w0;)
                   const float* buf = reinterpret_cast<const float*>(ring + (size_t)st * MK_STAGE);
                   const int nb = min(MK_SELF_KB, self_nblk - c * MK_SELF_KB);
 #pragma unroll
@@ -667,10 +677,13 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                       s8[c * 2 + u] = a0 + a1;
                     }
                   }
+                  MK_XP(const long long w2 = clock64(); xs_kmath += w2 - w1;)
                   gsync();
                   if (t == 0) mk_arrive(bar_empty + 8 * st);
+                  MK_XP(xs_sync += clock64() - w2;)
                 }
               }
+              MK_XP(xs_t = clock64();)
               float snew = 0.f;  // score of the token being appended
 #pragma unroll 8
               for (int d = 0; d < 64; ++d) snew += red_g[d];
@@ -703,12 +716,14 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               // P.V: thread (r4 = t / 16, c = t % 16) -> float4 column c over keys j == r4 (mod 4)
               const int r4 = t >> 4, cc = t & 15;
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              MK_XP(xs_soft += clock64() - xs_t;)
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 if (c < self_nvc) {
                   const int pos = r.s + (self_nkc + c) * ng + gi;
                   const int st = pos % MK_NST;
                   const uint32_t par = r.ph ^ (uint32_t)((pos / MK_NST) & 1);
+                  MK_XP(const long long w0 = clock64();)
                   {
                     const int seq = r.n + (self_nkc + c) * ng + gi;
                     uint32_t spins = 0;
@@ -716,6 +731,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                       if (++spins > (1u << 26)) mk_die(4, (uint32_t)seq, (uint32_t)*s_issued);
                   }
                   mk_wait(bar_full + 8 * st, par);
+                  MK_XP(const long long w1 = clock64(); xs_wait += w1 - w0;)
                   const float4* buf4 = reinterpret_cast<const float4*>(ring + (size_t)st * MK_STAGE);
                   const int m0 = c * MK_SELF_VR, rows = min(MK_SELF_VR, step - m0);
 #pragma unroll 4
@@ -724,10 +740,13 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                     const float pj = sc_g[m0 + jj];
                     acc.x += pj * vv.x; acc.y += pj * vv.y; acc.z += pj * vv.z; acc.w += pj * vv.w;
                   }
+                  MK_XP(const long long w2 = clock64(); xs_vmath += w2 - w1;)
                   gsync();
                   if (t == 0) mk_arrive(bar_empty + 8 * st);
+                  MK_XP(xs_sync += clock64() - w2;)
                 }
               }
+              MK_XP(xs_t = clock64();)
               // combine the four key residues: lanes l and l+16 inside a warp, then the two warps through shared memory
               acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
               acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
@@ -743,9 +762,15 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                 *reinterpret_cast<float4*>(p.ctx + (int64_t)b * D + h * 64 + 4 * lane) = o;
               }
               gsync();  // this group's shared scratch is reusable
+              MK_XP(xs_tail += clock64() - xs_t; xs_t = clock64();)
             }
             r.adv_n(nch * ng);
           }
+          MK_XP(if (p.prof && gi == 0 && t == 0 && l == NL / 2) {
+            unsigned long long* q = p.prof + ((size_t)g * 512 + 464) * 2;
+            q[0] = xs_wait; q[1] = xs_kmath; q[2] = xs_vmath; q[3] = xs_sync; q[4] = xs_head; q[5] = xs_soft; q[6] = xs_tail;
+            q[7] = clock64() - xs_begin;
+          })
         } else if (l < NL && ph == MK_PH_CROSS) {
           // ---------------------------------------------------------------------------------- cross-attention
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
@@ -799,7 +824,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
                 const int pitch = Mp >> 2;
                 // (the loop exists once per warp-uniform case so that its body is branch-free: loads first, then arithmetic)
                 auto k_rows = [&](auto both) {
-#pragma unroll 2
+MK_PRAGMA(unroll MK_XUNROLL)
                   for (int rr = 0; rr < rows_math; ++rr) {
                     const float qd = s_q[r0 + rr];
                     const uint2 h0 = hrow[0];
@@ -919,7 +944,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
               const int m0 = c * cross_vr, rows = min(cross_vr, Mp - m0);
               const uint8_t* hp = buf + c8 * 16;
               const uint8_t* lp = buf + (size_t)rows * 128 + c8 * 8;
-#pragma unroll 2
+MK_PRAGMA(unroll MK_XUNROLL)
               for (int jj = (p.dbg & 16) ? rows : r32; jj < rows; jj += 32) {  // MG_MEGA_DBG bit 4: stream only, no V-pass arithmetic
                 const uint4 hh = *reinterpret_cast<const uint4*>(hp + (size_t)jj * 128);
                 const uint2 ll = *reinterpret_cast<const uint2*>(lp + (size_t)jj * 64);

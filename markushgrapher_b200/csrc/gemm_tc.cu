@@ -472,7 +472,33 @@ struct alignas(64) SkinnyParams {
   // amax_val/amax_idx [B][gridDim.x]; ties resolve to the lowest feature index (torch.argmax semantics)
   float* amax_val;
   int* amax_idx;
+  const float* rs_in;  // pro == 1: row scales rsqrt(mean(x^2) + eps) * scale computed by rms_rowscale_kernel (null: in-kernel)
 };
+
+// RMSNorm row scales of up to 128 activation rows, one warp per row -- the same arithmetic, in the same order, as the
+// statistic warps of skinny_tc_kernel.  With more than 32 rows every CTA of the linear would recompute all of them (16
+// dependent round trips to L2 for 128 rows: +10 us on a 12 us kernel), so the wide launches get them from here.
+__global__ void __launch_bounds__(256) rms_rowscale_kernel(const float* __restrict__ x, int ldx, int B, int K, float eps,
+                                                           float scale, float* __restrict__ rs) {
+  griddep_launch();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  griddep_wait();
+  if (r >= B) return;
+  const int n4row = K >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)r * ldx);
+  float4 qa[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qa[i] = xr[min(lane + 32 * i, n4row - 1)];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 v = qa[i];
+    ss += (lane + 32 * i < n4row) ? (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w) : 0.f;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) rs[r] = rsqrtf(ss / (float)K + eps) * scale;
+}
 
 template <int NG>
 __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant__ SkinnyParams p) {
@@ -574,7 +600,9 @@ __global__ void __launch_bounds__(320, 1) skinny_tc_kernel(const __grid_constant
     const int t = threadIdx.x - 192;
     const int wq = warp - 6;  // 0..3
     griddep_wait();
-    if (p.pro == 1) {
+    if (p.pro == 1 && p.rs_in) {
+      if (t < R) s_rs[t] = p.rs_in[min(t, p.B - 1)];
+    } else if (p.pro == 1) {
       // K <= 1024 here (d_model).  Warp wq owns rows wq, wq + 4, ...: a lane holds 8 float4 of a row, two rows (16
       // loads) are in flight per round trip to L2, and a row's sum never leaves its warp -- no block-level combine.
       const int n4row = p.K >> 2;
@@ -752,7 +780,7 @@ static void launch_skinny_ng(cudaStream_t st, const SkinnyParams& p, dim3 grid) 
 
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
-                      bool store, float* amax_val, int* amax_idx) {
+                      bool store, float* amax_val, int* amax_idx, float* rs_scratch) {
   MG_REQUIRE(amax_val == nullptr || (store && amax_idx != nullptr), "fused argmax needs the direct-store (no split-K) mode");
   MG_REQUIRE(K % BK == 0 && ldx % 4 == 0, "skinny linear: K must be a multiple of 64");
   MG_REQUIRE(pro != 1 || K <= 1024, "skinny linear: fused RMSNorm needs K <= 1024");
@@ -783,6 +811,11 @@ void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes 
   p.pro = pro; p.lnw = lnw; p.eps = eps; p.scale = scale;
   p.zero_ptr = zero_ptr; p.zero_n = zero_n; p.store = store ? 1 : 0;
   p.amax_val = amax_val; p.amax_idx = amax_idx;
+  p.rs_in = nullptr;
+  if (pro == 1 && B > 32 && rs_scratch) {  // wide launch: row scales once, not once per CTA
+    launch_pdl(rms_rowscale_kernel, dim3((B + 7) / 8), dim3(256), (size_t)0, st, x, ldx, B, K, eps, scale, rs_scratch);
+    p.rs_in = rs_scratch;
+  }
   dim3 grid(tiles, ksplit);
   if (B <= 32) launch_skinny_ng<1>(st, p, grid);
   else if (B <= 64) launch_skinny_ng<2>(st, p, grid);

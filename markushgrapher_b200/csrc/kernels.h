@@ -133,7 +133,9 @@ void launch_beam_finalize(cudaStream_t st, const BeamState& s, int pad, int64_t*
 // gemm_tc.cu: tensor-core skinny linear with fused prologue (pro: 0 none, 1 RMSNorm, 2 ReLU), split-K atomics
 void launch_skinny_tc(cudaStream_t st, int pro, const float* x, int ldx, Planes W, int64_t ldw, float* out, int ld_out,
                       int B, int N, int K, const float* lnw, float eps, float scale, float* zero_ptr, int64_t zero_n,
-                      bool store, float* amax_val = nullptr, int* amax_idx = nullptr);
+                      bool store, float* amax_val = nullptr, int* amax_idx = nullptr, float* rs_scratch = nullptr);
+// (rs_scratch: >= B floats of device scratch; with more than 32 rows and a fused RMSNorm the row scales are computed once
+//  by a small kernel in front of the linear instead of by every CTA of it)
 
 // ---- pack.cu: GPU input packing (Pillow-exact resize + image-processor normalisation)
 int resample_coeffs(int in_size, int out_size, int filter, std::vector<int>& bounds, std::vector<int>& kk);

@@ -1109,6 +1109,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   unsigned long long* step_ts = a.get<unsigned long long>(max_length);  // %globaltimer at the end of every step
   int* gathered = a.get<int>((int64_t)world * B);
   int* gfinished = a.get<int>((int64_t)world * B);
+  float* rs_rows = a.get<float>(B);
 
   // ---- micro-batch lanes (experimental, MG_LANES=2; default 1).  The decode chain of one token is strictly
   // sequential and alternates between latency-bound kernels (skinny linears) and the HBM-bound cross-attention
@@ -1230,6 +1231,7 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
       launches += 2;
       return;
     }
+    float* const rs_scratch = rs_rows;  // RMSNorm row scales of the wide (> 32 rows) launches
     auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
                    float scale, float* zp, int64_t zn, bool store, bool amax = false) {
       for (int r0 = 0; r0 < bn; r0 += 128) {
@@ -1237,8 +1239,8 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
         launch_skinny_tc(ls, pro, xin + (int64_t)(b0 + r0) * ldx, ldx, W.w, W.ldk, out + (int64_t)(b0 + r0) * ld_out,
                          ld_out, bc, W.N, W.K, lnw, c.ln_eps, scale, r0 == 0 ? zp : nullptr, zn, store,
                          amax ? part_val + (int64_t)(b0 + r0) * n_part : nullptr,
-                         amax ? part_idx + (int64_t)(b0 + r0) * n_part : nullptr);
-        ++launches;
+                         amax ? part_idx + (int64_t)(b0 + r0) * n_part : nullptr, rs_scratch + b0 + r0);
+        launches += (pro == 1 && bc > 32) ? 2 : 1;
       }
     };
     for (int l = 0; l < NL; ++l) {
@@ -1476,13 +1478,14 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
   MG_CHECK_CUDA(cudaMemsetAsync(q, 0, sizeof(float) * (size_t)R * d, st));
   MG_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * (size_t)R * c.d_ff, st));
 
+  float* rs_rows = a.get<float>(R);  // RMSNorm row scales of the wide (> 32 rows) launches
   auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
                  float scale, float* zp, int64_t zn, bool store) {
     for (int b0 = 0; b0 < R; b0 += 128) {
       const int bc = std::min(128, R - b0);
       launch_skinny_tc(st, pro, xin + (int64_t)b0 * ldx, ldx, W.w, W.ldk, out + (int64_t)b0 * ld_out, ld_out, bc, W.N,
-                       W.K, lnw, c.ln_eps, scale, b0 == 0 ? zp : nullptr, zn, store);
-      ++launches;
+                       W.K, lnw, c.ln_eps, scale, b0 == 0 ? zp : nullptr, zn, store, nullptr, nullptr, rs_rows + b0);
+      launches += (pro == 1 && bc > 32) ? 2 : 1;
     }
   };
   auto one_step = [&]() {

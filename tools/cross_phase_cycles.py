@@ -25,3 +25,11 @@ print(f"  {'unaccounted':28s} {us(rest).mean():7.2f}")
 pa = prod[:, 2] > 0
 print(f"producer, microseconds per phase (mean): wait for a free stage {us(prod[pa, 0]).mean():.2f}, issue {us(prod[pa, 1]).mean():.2f} "
       f"({us(prod[pa, 1] / prod[pa, 2]).mean() * 1e3:.0f} ns per chunk), chunks {prod[pa, 2].mean():.1f}")
+
+sf = a[:, 928:936].astype(np.float64)   # slot 464: self-attention phase, group 0 thread 0
+sa = sf[:, 7] > 0
+if sa.any():
+    print(f"self-attention phase (group 0 of {int(sa.sum())} CTAs), microseconds per phase (mean / max); total {us(sf[sa, 7]).mean():.2f} / {us(sf[sa, 7]).max():.2f}")
+    for i, nm in enumerate(["wait for data", "K arithmetic", "V arithmetic", "group barrier+release", "item head (q/k/v, bias loads)", "softmax", "item tail (combine, ctx)"]):
+        print(f"  {nm:30s} {us(sf[sa, i]).mean():7.2f} / {us(sf[sa, i]).max():7.2f}")
+    print(f"  {'unaccounted':30s} {us(sf[sa, 7] - sf[sa, :7].sum(axis=1)).mean():7.2f}")
