@@ -459,6 +459,40 @@ struct mg_model {
     ++launches;
   }
 
+  // Decode-chain linear for MORE than 128 activation rows (beam search over large batches, batches > 128 per GPU;
+  // measured: 500 rows 18.7 -> 13.4 ms per step, but 128 rows 6.37 -> 6.66, so one skinny launch keeps those): the activations are
+  // normalised / rectified and split into planes ONCE by a small kernel, then the persistent TMA-fed tcgen05 GEMM runs
+  // with the weights on the M axis and split-K atomics into the output -- instead of skinny_tc_kernel<4>, where every
+  // CTA re-loads and re-splits the whole activation tile (one L2 round trip per k-block) and launches of 128 rows each
+  // re-read the weights.  out[b][n] += sum_k pro(x)[b][k] W[n][k];  pro: 0 none, 1 RMSNorm (weight lnw), 2 ReLU.
+  int wide_linear(cudaStream_t st, int pro, const float* x, int ldx, const LinearW& W, float* out, int ld_out,
+                  const float* lnw, float scale, int rows, Planes xs, float* zero_ptr, int64_t zero_n) {
+    int n = 0;
+    if (pro == 1) {
+      MG_REQUIRE(ldx == W.K, "wide linear: RMSNorm input must be contiguous rows");
+      launch_rmsnorm(st, x, lnw, rows, W.K, cfg.ln_eps, scale, xs, nullptr, 0, 0, 0);
+    } else if (pro == 2) {
+      MG_REQUIRE(ldx == W.K, "wide linear: ReLU input must be contiguous rows");
+      launch_relu_split(st, x, (int64_t)rows * W.K, xs);
+    } else {
+      launch_split(st, x, rows, W.K, ldx, xs, W.K);
+    }
+    ++n;
+    if (zero_ptr) MG_CHECK_CUDA(cudaMemsetAsync(zero_ptr, 0, sizeof(float) * (size_t)zero_n, st));
+    GemmOperand A, B;
+    A.hi = W.w.hi; A.lo = W.w.lo; A.rows = W.N; A.ld = W.ldk;
+    B.hi = xs.hi; B.lo = xs.lo; B.rows = rows; B.ld = W.K;
+    GemmEpilogue ep;
+    ep.out_f32 = out;
+    ep.ld_r = 1;        // feature index (GEMM row) is the fast axis of out[b][n]
+    ep.ld_c = ld_out;   // activation row (GEMM column) strides by the output's leading dimension
+    ep.atomic = 1;
+    const int tiles = ((W.N + 127) / 128) * ((rows + 127) / 128);
+    const int ksplit = std::max(1, std::min((W.K + 63) / 64, 148 / std::max(1, tiles)));
+    launch_gemm(st, A, B, W.N, rows, W.K, 1, 1, ksplit, ep, 128);
+    return n + 1;
+  }
+
   void finalize(cudaStream_t st);
   void encode(cudaStream_t st, int B, int Lt, const int64_t* ids, const float* bbox, const float* px,
               const int64_t* amask);
@@ -1119,6 +1153,9 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
   // as the full-batch ones and contend for shared memory -- so the default stays at one lane.
   static const int env_lanes = getenv("MG_LANES") ? atoi(getenv("MG_LANES")) : 1;
   const int nlanes = (B >= 8 && env_lanes >= 2 && !use_mega) ? 2 : 1;
+  // wide batches (> 128 rows, kernel chain, one lane): activation planes of the linears' inputs (MG_WIDE=0: skinny kernels only)
+  const bool wide = split2 && nlanes == 1 && !(getenv("MG_WIDE") && getenv("MG_WIDE")[0] == '0');
+  Planes wide_xs = (wide && B > 128) ? planes(a, (int64_t)B * std::max(d, c.d_ff)) : Planes{};
   struct Lane {
     int b0, bn;
     cudaStream_t st;
@@ -1234,6 +1271,11 @@ void mg_model::generate(cudaStream_t st, int B, int max_length, int64_t* out_ids
     float* const rs_scratch = rs_rows;  // RMSNorm row scales of the wide (> 32 rows) launches
     auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
                    float scale, float* zp, int64_t zn, bool store, bool amax = false) {
+      if (wide && bn > 128 && !store) {
+        launches += wide_linear(ls, pro, xin + (int64_t)b0 * ldx, ldx, W, out + (int64_t)b0 * ld_out, ld_out, lnw, scale, bn,
+                                wide_xs, zp, zn);
+        return;
+      }
       for (int r0 = 0; r0 < bn; r0 += 128) {
         const int bc = std::min(128, bn - r0);
         launch_skinny_tc(ls, pro, xin + (int64_t)(b0 + r0) * ldx, ldx, W.w, W.ldk, out + (int64_t)(b0 + r0) * ld_out,
@@ -1479,8 +1521,14 @@ void mg_model::generate_beam(cudaStream_t st, int B, int nb, int max_length, int
   MG_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * (size_t)R * c.d_ff, st));
 
   float* rs_rows = a.get<float>(R);  // RMSNorm row scales of the wide (> 32 rows) launches
+  const bool wide = split2 && !(getenv("MG_WIDE") && getenv("MG_WIDE")[0] == '0');
+  Planes wide_xs = (wide && R > 128) ? planes(a, (int64_t)R * std::max(d, c.d_ff)) : Planes{};
   auto lin = [&](int pro, const float* xin, int ldx, const LinearW& W, float* out, int ld_out, const float* lnw,
                  float scale, float* zp, int64_t zn, bool store) {
+    if (wide && R > 128 && !store) {
+      launches += wide_linear(st, pro, xin, ldx, W, out, ld_out, lnw, scale, R, wide_xs, zp, zn);
+      return;
+    }
     for (int b0 = 0; b0 < R; b0 += 128) {
       const int bc = std::min(128, R - b0);
       launch_skinny_tc(st, pro, xin + (int64_t)b0 * ldx, ldx, W.w, W.ldk, out + (int64_t)b0 * ld_out, ld_out, bc, W.N,

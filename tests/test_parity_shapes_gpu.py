@@ -102,9 +102,10 @@ def test_bench_workload_full_511_steps_rows_vs_oracle(full_pair):
 
 
 # ------------------------------------------------------------------------------------------------ (b)
-@pytest.mark.parametrize("B", [48, 128])
+@pytest.mark.parametrize("B", [48, 128, 144])
 def test_activation_rows_33_to_128_vs_oracle(B):
-    """B > 32 runs the kernel chain with skinny_tc_kernel<2> (33..64 rows) / <4> (65..128 rows)"""
+    """B > 32 runs the kernel chain with skinny_tc_kernel<2> (33..64 rows) / <4> (65..128 rows); more than 128 rows take
+    the split-once + persistent tcgen05 GEMM route (model.cu wide_linear) with skinny launches of 128 rows for the LM head"""
     cfg = O.MGConfig.small()
     oracle = O.build(cfg, seed=0)
     inp = O.make_inputs(cfg, B, 16, seed=100 + B, ragged=True)
@@ -120,8 +121,8 @@ def test_activation_rows_33_to_128_vs_oracle(B):
 
 @pytest.mark.parametrize("B,nb", [(12, 5), (24, 5), (40, 4)])
 def test_beam_rows_33_to_160_vs_stock_beam_search(B, nb):
-    """beam search with more than 32 decoder rows (B x beams = 60 / 120 / 160: skinny_tc_kernel<2> / <4> and the
-    128-row launch split) and the kv24 cross K/V shared by an image's beams, against GenerationMixin._beam_search"""
+    """beam search with more than 32 decoder rows (B x beams = 60 / 120 / 160: skinny_tc_kernel<2> / <4>, and at 160
+    rows the wide-linear GEMM route) and the kv24 cross K/V shared by an image's beams, against GenerationMixin._beam_search"""
     cfg = O.MGConfig.small()
     oracle = O.build(cfg, seed=0)
     inp = O.make_inputs(cfg, B, 14, seed=300 + B, ragged=True)
