@@ -147,7 +147,7 @@ void launch_beam_self_attn(cudaStream_t st, const float* qkv, int R, int H, int 
 // =====================================================================================================
 // streaming cross-attention, one CTA per (head, IMAGE) serving nq <= 8 queries (the image's beams) from a single
 // pass over the K^T / V blocks.  Same pipeline as cross_attn_stream_kernel (decode.cu).
-constexpr int BC_STAGE_BYTES = 15360;
+constexpr int BC_STAGE_BYTES = 24576;  // (15360 until round 2: fewer, larger chunks -- the per-chunk hand-off is what a streaming attention kernel pays for)
 constexpr int BC_NST = 3;
 constexpr int BC_MAXK = 8;
 
@@ -343,7 +343,7 @@ void launch_beam_cross_attn(cudaStream_t st, const float* q, int B, int nq, int 
 
 // kv24 variant (decode.cu: 16-bit + 8-bit planes, 3 bytes per element, the format the greedy paths stream): one CTA
 // per (head, IMAGE), the image's block streamed ONCE for its nq beams -- per generated token a beam-4 decode moves
-// 3/16 of the bytes of the reference's nb-times-repeated fp32 encoder K/V.  Scores: thread = pair of adjacent keys.
+// 3/16 of the bytes of the reference's nb-times-repeated fp32 encoder K/V.  Scores: thread = quad of adjacent keys.
 __global__ void __launch_bounds__(288) beam_cross_attn24_kernel(const float* __restrict__ q, const uint8_t* __restrict__ kv,
                                                                 const int* __restrict__ mask, int Mp, int H, int D,
                                                                 int nq, float* __restrict__ ctx) {
@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(288) beam_cross_attn24_kernel(const float* __r
   asm volatile("bar.sync 1, 256;" ::: "memory");
   int s = 0;
   uint32_t ph = 0;
-  const int npair = Mp >> 1;
-  float acc[BM_MAXNB][BC_MAXK];  // acc[k][2i], acc[k][2i+1] = keys 2*(tid + 256 i), +1 of beam k
+  const bool kq0 = 128 * warp < Mp, kq1 = 1024 + 128 * warp < Mp;  // this warp's key quads exist (warp-uniform)
+  float acc[BM_MAXNB][BC_MAXK];  // acc[k][i] = key 4 * tid + (i & 3) + 1024 * (i >> 2) of beam k
 #pragma unroll
   for (int k = 0; k < BM_MAXNB; ++k)
 #pragma unroll
@@ -419,16 +419,28 @@ __global__ void __launch_bounds__(288) beam_cross_attn24_kernel(const float* __r
     const int r0 = c * RK, rows = min(RK, HD - r0);
     const uint8_t* lo_base = buf + (size_t)rows * Mp * 2;
     for (int rr = 0; rr < rows; ++rr) {
-      const uint32_t* hrow = reinterpret_cast<const uint32_t*>(buf + (size_t)rr * Mp * 2);
-      const uint16_t* lrow = reinterpret_cast<const uint16_t*>(lo_base + (size_t)rr * Mp);
+      // thread = 4 adjacent keys (+ the 4 keys 1024 further on): an 8-byte load of the 16-bit plane and a 4-byte load of
+      // the 8-bit plane per quad (3 shared-memory wavefronts per 128 keys; key pairs with 2-byte loads needed 4 and ran
+      // every warp over all 2048 key slots -- decode_mega.cu, DESIGN.md decision 10).  kq0 / kq1 are warp-uniform; lanes
+      // past the row's end inside an active warp read the next row / plane, their sums are never used.
+      const uint2* hrow = reinterpret_cast<const uint2*>(buf + (size_t)rr * Mp * 2) + tid;
+      const uint32_t* lrow = reinterpret_cast<const uint32_t*>(lo_base + (size_t)rr * Mp) + tid;
       float kvv[BC_MAXK];
-#pragma unroll
-      for (int i = 0; i < BC_MAXK / 2; ++i) {
-        const int pi = tid + 256 * i;
-        uint32_t h2 = 0u, l2 = 0u;
-        if (pi < npair) { h2 = hrow[pi]; l2 = lrow[pi]; }
-        kvv[2 * i] = __uint_as_float(__byte_perm(h2, l2, 0x1046));
-        kvv[2 * i + 1] = __uint_as_float(__byte_perm(h2, l2, 0x3256));
+      uint2 h0 = make_uint2(0u, 0u), h1 = make_uint2(0u, 0u);
+      uint32_t l0 = 0u, l1 = 0u;
+      if (kq0) { h0 = hrow[0]; l0 = lrow[0]; }
+      if (kq1) { h1 = hrow[256]; l1 = lrow[256]; }
+      {
+        const uint32_t la = __byte_perm(l0, 0u, 0x4240), lb = __byte_perm(l0, 0u, 0x4341);
+        kvv[0] = __uint_as_float(__byte_perm(h0.x, la, 0x1045));
+        kvv[1] = __uint_as_float(__byte_perm(h0.x, lb, 0x3245));
+        kvv[2] = __uint_as_float(__byte_perm(h0.y, la, 0x1065));
+        kvv[3] = __uint_as_float(__byte_perm(h0.y, lb, 0x3265));
+        const uint32_t lc = __byte_perm(l1, 0u, 0x4240), ld = __byte_perm(l1, 0u, 0x4341);
+        kvv[4] = __uint_as_float(__byte_perm(h1.x, lc, 0x1045));
+        kvv[5] = __uint_as_float(__byte_perm(h1.x, ld, 0x3245));
+        kvv[6] = __uint_as_float(__byte_perm(h1.y, lc, 0x1065));
+        kvv[7] = __uint_as_float(__byte_perm(h1.y, ld, 0x3265));
       }
 #pragma unroll
       for (int k = 0; k < BM_MAXNB; ++k) {
@@ -451,7 +463,7 @@ __global__ void __launch_bounds__(288) beam_cross_attn24_kernel(const float* __r
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < BC_MAXK; ++i) {
-        const int m = 2 * (tid + 256 * (i >> 1)) + (i & 1);
+        const int m = 4 * tid + (i & 3) + 1024 * (i >> 2);
         if (m < Mp) {
           acc[k][i] += (mask[(int64_t)b * Mp + m] ? 0.f : -3.4028234663852886e38f);
           mx = fmaxf(mx, acc[k][i]);
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(288) beam_cross_attn24_kernel(const float* __r
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < BC_MAXK; ++i) {
-        const int m = 2 * (tid + 256 * (i >> 1)) + (i & 1);
+        const int m = 4 * tid + (i & 3) + 1024 * (i >> 2);
         if (m < Mp) {
           const float p = expf(acc[k][i] - mx);
           sc[(int64_t)k * Mp + m] = p;
