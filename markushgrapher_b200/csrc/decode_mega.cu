@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
   float* const s_b = reinterpret_cast<float*>(ring + MK_OFF_SB);
   volatile int* const s_phase = reinterpret_cast<volatile int*>(ring + MK_OFF_SB + 32);
   volatile int* const s_issued = reinterpret_cast<volatile int*>(ring + MK_OFF_SB + 36);  // loads the producer has issued
+  int* const s_rel = reinterpret_cast<int*>(ring + MK_OFF_SB + 40);  // [MK_NST] cross-attention: consumer warps done with a stage
   const uint32_t ring_a = smem_u32(ring);
   const uint32_t bar_full = ring_a + MK_OFF_BAR, bar_empty = bar_full + 8 * MK_NST, bar_xrdy = bar_empty + 8 * MK_NST;
   const uint32_t bar_tfull = bar_xrdy + 8 * MK_NST, bar_tempty = bar_tfull + 8;
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
     mbar_init(reinterpret_cast<uint64_t*>(ring + MK_OFF_BAR) + 3 * MK_NST + 1, 256);
     *s_phase = 0;  // phase the consumers have entered (prefetch gate)
     *s_issued = 0;
+    for (int i = 0; i < MK_NST; ++i) s_rel[i] = 0;
     fence_mbar_init();
     if (g == 0) p.bar_ctr[(step + 1) & 1] = 0u;  // the other parity's counter is idle during this launch
     if (g == 0) g_mk_dbg = p.dbg_host;
@@ -776,6 +778,22 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
           // kv24 K^T / V blocks (decode.cu: 16-bit + 8-bit planes, 3 bytes per element); additive mask
           // (1-mask)*finfo.min, no positional bias, no scale.  Scores: thread = quad of adjacent keys.
           const unsigned x_epoch = (unsigned)(step * NL + l + 1);  // unique per (step, layer): the flags need no reset
+          // A chunk's stage is handed back after a 256-thread barrier.  (-DMK_WARPREL, measured experiment: the LAST of the
+          // eight consumer warps to finish a chunk hands it back through a shared-memory counter, so the warps may drift
+          // apart inside a pass -- 2.132 instead of 2.103 ms per step: the counter's atomics and the lost lockstep cost
+          // more than the barrier.)
+          auto cross_release = [&]() {
+#ifdef MK_WARPREL
+            __syncwarp();
+            if (lane == 0 && atomicAdd(s_rel + r.s, 1) == 7) {
+              s_rel[r.s] = 0;  // the stage cannot be refilled and finished by eight warps again before this arrive
+              mk_arrive(bar_empty + 8 * r.s);
+            }
+#else
+            cons_sync();
+            if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
+#endif
+          };
           int rs_b = -1;    // image whose row scale rsb holds: consecutive entries are mostly heads of one image
           float rsb = 0.f;
           MK_XP(long long xc_wait = 0, xc_math = 0, xc_sync = 0, xc_head = 0, xc_soft = 0, xc_tail = 0, xc_n = 0;
@@ -851,8 +869,7 @@ MK_PRAGMA(unroll MK_XUNROLL)
                 if (kq1) k_rows(std::true_type{});
                 else if (kq0) k_rows(std::false_type{});
                 MK_XP(const long long w2 = clock64(); xc_math += w2 - w1;)
-                cons_sync();
-                if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
+                cross_release();
                 r.adv();
                 MK_XP(xc_sync += clock64() - w2;)
               }
@@ -961,8 +978,7 @@ MK_PRAGMA(unroll MK_XUNROLL)
                 av[7] += pj * __uint_as_float(__byte_perm(hh.w, ld, 0x3265));
               }
               MK_XP(const long long w2 = clock64(); xc_math += w2 - w1;)
-              cons_sync();
-              if (ct == 0) mk_arrive(bar_empty + 8 * r.s);
+              cross_release();
               r.adv();
               MK_XP(xc_sync += clock64() - w2;)
             }
