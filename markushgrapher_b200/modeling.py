@@ -197,6 +197,12 @@ class MarkushgrapherForConditionalGeneration(nn.Module):
             self._engine_key = key
         return self._engine
 
+    @property
+    def engine(self) -> MGEngine:
+        """the device engine behind this model (built on first use): `encode_ahead` / `generate_host` / ... for callers that
+        want more than the reference's `generate` contract"""
+        return self._get_engine()
+
     @torch.no_grad()
     def generate(self, input_ids=None, bbox=None, pixel_values=None, attention_mask=None, labels=None,
                  num_beams: int = 1, max_length: int = 512, **kwargs) -> torch.Tensor:
