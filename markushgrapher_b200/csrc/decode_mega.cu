@@ -1151,10 +1151,24 @@ MK_PRAGMA(unroll MK_XUNROLL)
 #endif
 #pragma unroll
               for (int i = 0; i < 4; ++i) v[i] = ldcg4(xk + (int64_t)min(r8 + i * 8, B - 1) * ldx);
+#ifdef MK_XPF2
+              // experiment build: the activation tiles travel TWO k-blocks ahead of the staging (one more L2 round trip hidden)
+              float4 v1[4], g1 = make_float4(1.f, 1.f, 1.f, 1.f);
+              {
+                const int k1 = min(1, nkb - 1) * 64;
+                if (pro == 1) g1 = *reinterpret_cast<const float4*>(lnw + kb0 * 64 + k1 + c4 * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v1[i] = ldcg4(xk + k1 + (int64_t)min(r8 + i * 8, B - 1) * ldx);
+              }
+#endif
 #pragma unroll 1
               for (int kb = 0; kb < nkb; ++kb) {
                 float4 vn[4], gn = make_float4(1.f, 1.f, 1.f, 1.f);
+#ifdef MK_XPF2
+                const int kn = min(kb + 2, nkb - 1) * 64;
+#else
                 const int kn = min(kb + 1, nkb - 1) * 64;  // prefetch the next k-block while this one is staged
+#endif
                 if (pro == 1) gn = *reinterpret_cast<const float4*>(lnw + kb0 * 64 + kn + c4 * 4);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) vn[i] = ldcg4(xk + kn + (int64_t)min(r8 + i * 8, B - 1) * ldx);
@@ -1186,9 +1200,16 @@ MK_PRAGMA(unroll MK_XUNROLL)
                 fence_proxy_async();
                 mk_arrive(bar_xrdy + 8 * r.s);
                 r.adv();
+#ifdef MK_XPF2
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { v[i] = v1[i]; v1[i] = vn[i]; }
+                gw = g1;
+                g1 = gn;
+#else
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[i] = vn[i];
                 gw = gn;
+#endif
               }
             } else {
               r.adv_n(nkb);  // keep this warp's view of the ring in step with the workers / the MMA warp
