@@ -1803,8 +1803,12 @@ int mg_generate(mg_model* m, void* stream, int B, int Lt, const int64_t* input_i
   // a batch whose encoder ran ahead (mg_encode_ahead) is taken from its slot; while ANOTHER batch is being encoded ahead
   // this call runs on the large SM partition, so that the two never compete for an SM
   const int slot = m->find_ahead(B, Lt, input_ids, bbox, pixel_values, attn_mask);
-  bool other_pending = false;
-  for (int i = 0; i < 2; ++i) other_pending = other_pending || (i != slot && m->ahead[i].valid);
+  bool other_pending = false;  // ... and its encoder has not finished yet (a finished one needs no SMs any more)
+  for (int i = 0; i < 2; ++i) {
+    if (i == slot || !m->ahead[i].valid) continue;
+    if (cudaEventQuery(m->ahead[i].done) != cudaSuccess) other_pending = true;
+    cudaGetLastError();  // (cudaErrorNotReady is an answer, not an error)
+  }
   m->run_ctas = 0;
   // NCCL collectives inside the decode loop (beam search across ranks, MG_DIST=nccl) stay on the caller's stream: let the
   // run-ahead encoder finish first instead of partitioning
