@@ -272,7 +272,9 @@ __global__ void __launch_bounds__(MK_THREADS, MK_OCC) decode_step_kernel(const _
   const int self_nblk = (step + 31) >> 5;
   const int self_nkc = (self_nblk + MK_SELF_KB - 1) / MK_SELF_KB;
   const int self_nvc = (step + MK_SELF_VR - 1) / MK_SELF_VR;
-  int cross_rk = min(64, (MK_STAGE / (Mp * 3)) & ~1);  // d-rows per K chunk, even (16-byte sized copies)
+  // d-rows per K chunk: both planes' copies must be 16-byte sized and aligned -- any count if Mp is a multiple of 16 (the
+  // compacted memory is padded to that), else an even one
+  int cross_rk = (Mp & 15) == 0 ? min(64, MK_STAGE / (Mp * 3)) : min(64, (MK_STAGE / (Mp * 3)) & ~1);
   int cross_vr = MK_CROSS_VR;
   // experiment switches (MG_MEGA_CROSS_RK / MG_MEGA_CROSS_VR): smaller chunks = emptier ring stages
   if (p.cross_rk > 0) cross_rk = max(2, min(cross_rk, p.cross_rk & ~1));

@@ -1039,7 +1039,7 @@ void mg_model::prepare_decoder_memory(cudaStream_t st, int B) {
   MG_CHECK_CUDA(cudaStreamSynchronize(st));
   int mx = 1;
   for (int v : h) mx = std::max(mx, v);
-  const int Mc = (int)rup(mx, 8);
+  const int Mc = (int)rup(mx, getenv("MG_COMPACT_PAD8") ? 8 : 16);  // 16: the fused step's K chunks may then hold an odd number of d-rows
   if (Mc >= cur_Mp) return;  // nothing to drop
   dM = mx;
   dMp = Mc;
